@@ -1,0 +1,44 @@
+"""Shared test plumbing: import paths, the `gpu` marker, golden-vector loading."""
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+REPO = Path(__file__).resolve().parent.parent
+PKG_ROOT = REPO / "copula-msm-and-copula-garch-var_b200"
+for p in (str(PKG_ROOT), str(REPO)):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+GOLDEN_DIR = REPO / "tests" / "golden"
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+def golden_names():
+    return sorted(p.stem for p in GOLDEN_DIR.glob("*.npz"))
+
+
+def load_golden(name):
+    """(HotPathInputs, npz dict) of one golden case produced by tests/golden/make_golden.py."""
+    from cvar_b200.inputs import HotPathInputs
+
+    g = dict(np.load(GOLDEN_DIR / f"{name}.npz"))
+    marginal = str(g["marginal"])
+    kw = dict(sigma=g["sigma"]) if marginal == "single" else dict(probs=g["probs"], sigma_states=g["sigma_states"])
+    inp = HotPathInputs(copula=str(g["copula"]), marginal=marginal, n=int(g["n"]), x=g["ref_x"], dx=g["ref_dx"],
+                        weights=g["weights"], rho=float(g["rho"]), nu=float(g["nu"]), theta=float(g["theta"]),
+                        ptf_mean=float(g["ptf_mean"]), **kw)
+    return inp, g
+
+
+@pytest.fixture(scope="session")
+def cuda_device():
+    import torch
+
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    return torch.device("cuda:0")
