@@ -1,0 +1,575 @@
+// cvar_api.cu -- C ABI (include/cvar.h) over the sm_100a kernels in cvar_kernels.cuh.
+//
+// Host side only does: argument validation, run-constant preparation (copula constants, the
+// Student-t quantile table, the axis on the device), launches, and the H2D/D2H copies of the
+// `*_host` entry points.  There is no CPU implementation of the solve in this library.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "../../include/cvar.h"
+#include "cvar_kernels.cuh"
+
+using namespace cvar;
+
+// ---------------------------------------------------------------------------------------------
+struct cvar_plan {
+    cvar_desc_t desc;
+    KernelParams kp;
+    FinalizeParams fp;
+    int device;
+    int sm_count;
+    int ctas_per_sm;
+    size_t smem_bytes;
+    double tq_err;
+    double last_kernel_ms;
+    cudaStream_t stream;
+    cudaEvent_t ev0, ev1;
+    double* d_x;
+    double* d_dx;
+    double* d_sigma_states;
+    double* d_tq_table;
+    // growable workspace of the *_host entry points
+    void* d_ws;
+    size_t ws_bytes;
+    int* d_k;  // [CVAR_MAX_ALPHA] iteration counts
+};
+
+#define CU_TRY(expr)                          \
+    do {                                      \
+        cudaError_t _e = (expr);              \
+        if (_e != cudaSuccess) return (int)_e; \
+    } while (0)
+
+namespace {
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = false;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) == cudaSuccess && cudaSetDevice(dev) == cudaSuccess) ok = true;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+int needed_iterations(double width, double tol) {
+    // while (upper - lower > tol) halve   (utils/calc_var_class.py:278); widths are dyadic => exact
+    int k = 0;
+    while (width > tol && k < 64) {
+        width /= 2;
+        ++k;
+    }
+    return k;
+}
+
+template <typename K>
+int set_smem(K kernel, size_t bytes) {
+    return (int)cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
+
+int ensure_ws(cvar_plan* p, size_t bytes) {
+    if (bytes <= p->ws_bytes) return 0;
+    if (p->d_ws) CU_TRY(cudaFree(p->d_ws));
+    p->d_ws = nullptr;
+    p->ws_bytes = 0;
+    size_t want = std::max(bytes, (size_t)1 << 20);
+    CU_TRY(cudaMalloc(&p->d_ws, want));
+    p->ws_bytes = want;
+    return 0;
+}
+
+size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+__global__ void tq_table_check_kernel(double nu, const double* __restrict__ table, double tail_lc,
+                                      unsigned long long* __restrict__ max_err_bits) {
+    // off-node probes in every interval: table vs the iterative routine
+    const double probes[4] = {-0.83, -0.21, 0.37, 0.91};
+    const int m = blockIdx.x, k = threadIdx.x;
+    if (k >= 4) return;
+    const double h = TQ_WMAX / TQ_INTERVALS;
+    const double w = -TQ_WMAX + h * (m + 0.5 * (1.0 + probes[k]));
+    const double p = 0.5 * erfc(-w * 0.7071067811865476);
+    TDist D = tdist_make(nu);
+    const double exact = t_quantile_mag_iterative(D, p);
+    const double fast = t_quantile_mag_table(table, nu, tail_lc, p);
+    const double err = fabs(fast - exact) / exact;
+    atomicMax(max_err_bits, (unsigned long long)__double_as_longlong(err));  // err >= 0: bit order == value order
+}
+
+int launch_solve(cvar_plan* p, const double* d_day, int64_t T, const AlphaSet& A, uint32_t* d_traj, double* d_mass,
+                 unsigned long long* d_cells, cudaStream_t st) {
+    if (T == 0) return 0;
+    dim3 grid((unsigned)T), block(CTA_THREADS);
+    switch (p->desc.copula) {
+        case CVAR_COPULA_GAUSSIAN:
+            solve_kernel<0><<<grid, block, p->smem_bytes, st>>>(p->kp, d_day, (long long)T, A, d_traj, d_mass, d_cells);
+            break;
+        case CVAR_COPULA_STUDENT:
+            solve_kernel<1><<<grid, block, p->smem_bytes, st>>>(p->kp, d_day, (long long)T, A, d_traj, d_mass, d_cells);
+            break;
+        default:
+            solve_kernel<2><<<grid, block, p->smem_bytes, st>>>(p->kp, d_day, (long long)T, A, d_traj, d_mass, d_cells);
+    }
+    return (int)cudaGetLastError();
+}
+
+int launch_strip(cvar_plan* p, const double* d_day, int64_t T, const double* d_bounds, double* d_out,
+                 unsigned long long* d_cells, cudaStream_t st) {
+    if (T == 0) return 0;
+    dim3 grid((unsigned)T), block(CTA_THREADS);
+    switch (p->desc.copula) {
+        case CVAR_COPULA_GAUSSIAN:
+            strip_mass_kernel<0><<<grid, block, p->smem_bytes, st>>>(p->kp, d_day, d_bounds, d_out, d_cells);
+            break;
+        case CVAR_COPULA_STUDENT:
+            strip_mass_kernel<1><<<grid, block, p->smem_bytes, st>>>(p->kp, d_day, d_bounds, d_out, d_cells);
+            break;
+        default:
+            strip_mass_kernel<2><<<grid, block, p->smem_bytes, st>>>(p->kp, d_day, d_bounds, d_out, d_cells);
+    }
+    return (int)cudaGetLastError();
+}
+
+int launch_finalize(cvar_plan* p, const uint32_t* d_traj, int64_t T, int32_t n_alpha, const int32_t* forced,
+                    double ptf_mean, double* d_var, int32_t* d_case, cudaStream_t st) {
+    FinalizeParams F = p->fp;
+    F.ptf_mean = ptf_mean;
+    for (int i = 0; i < CVAR_MAX_ALPHA; ++i) F.forced[i] = (forced && i < n_alpha) ? forced[i] : -1;
+    finalize_reduce_kernel<<<n_alpha, 1024, 0, st>>>(F, d_traj, (long long)T, p->d_k);
+    CU_TRY(cudaGetLastError());
+    const long long total = (long long)T * n_alpha;
+    if (total > 0) {
+        finalize_apply_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(F, d_traj, (long long)T, n_alpha, p->d_k,
+                                                                              d_var, d_case);
+        CU_TRY(cudaGetLastError());
+    }
+    return 0;
+}
+
+int day_stride(const cvar_plan* p) { return p->desc.marginal == CVAR_MARGINAL_SINGLE ? 2 : 2 * p->desc.q; }
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+extern "C" {
+
+int cvar_abi_version(void) { return CVAR_ABI_VERSION; }
+
+void cvar_desc_default(cvar_desc_t* d) {
+    if (!d) return;
+    std::memset(d, 0, sizeof(*d));
+    d->struct_size = (uint32_t)sizeof(cvar_desc_t);
+    d->abi_version = CVAR_ABI_VERSION;
+    d->copula = CVAR_COPULA_GAUSSIAN;
+    d->marginal = CVAR_MARGINAL_SINGLE;
+    d->n = 100;  // utils/calc_var_class.py:16
+    d->q = 1;
+    d->compat_flags = CVAR_COMPAT_REFERENCE;
+    d->max_iter = 0;
+    d->rho = d->nu = d->theta = NAN;
+    d->w0 = d->w1 = 0.5;   // :17
+    d->clip_lo = -5.0;     // :201
+    d->neg_inf = -100.0;   // :114
+    d->first_guess = -3.0; // :95
+    d->second_lo = -3.5;
+    d->second_hi = -2.0;
+    d->min_var = -7.5;     // :111
+    d->max_var = 0.0;      // :112
+    d->tol = 1e-6;         // :257
+}
+
+const char* cvar_strerror(int status) {
+    switch (status) {
+        case CVAR_OK: return "ok";
+        case CVAR_ERR_NULL: return "required pointer is NULL";
+        case CVAR_ERR_COPULA: return "unknown copula or marginal family";
+        case CVAR_ERR_GRID: return "bad grid: need 2 <= n <= CVAR_MAX_N and a strictly ascending axis";
+        case CVAR_ERR_PARAM: return "parameter out of range (|rho| < 1, nu > 0, theta > 0, w0 != 0, 1 <= q <= CVAR_MAX_Q, finite sigmas)";
+        case CVAR_ERR_SIZE: return "bad size (T < 0 or n_alpha outside 1..CVAR_MAX_ALPHA)";
+        case CVAR_ERR_NO_DEVICE: return "no usable CUDA device (this library has no CPU fallback)";
+        case CVAR_ERR_ABI: return "cvar_desc_t struct_size / abi_version mismatch";
+        case CVAR_ERR_SMEM: return "grid too large for the shared memory of one SM";
+        default: break;
+    }
+    if (status > 0) return cudaGetErrorString((cudaError_t)status);
+    return "unknown status";
+}
+
+int cvar_plan_create(const cvar_desc_t* desc, const double* x, const double* dx, const double* sigma_states,
+                     int device, cvar_plan_t** out) {
+    if (!desc || !x || !dx || !out) return CVAR_ERR_NULL;
+    *out = nullptr;
+    if (desc->struct_size != sizeof(cvar_desc_t) || desc->abi_version != CVAR_ABI_VERSION) return CVAR_ERR_ABI;
+    if (desc->copula < 0 || desc->copula > 2 || desc->marginal < 0 || desc->marginal > 1) return CVAR_ERR_COPULA;
+    const int n = desc->n;
+    if (n < 2 || n > CVAR_MAX_N) return CVAR_ERR_GRID;
+    for (int i = 1; i < n; ++i)
+        if (!(x[i] > x[i - 1])) return CVAR_ERR_GRID;
+    for (int i = 0; i < n; ++i)
+        if (!std::isfinite(x[i]) || !std::isfinite(dx[i])) return CVAR_ERR_GRID;
+    const int q = desc->marginal == CVAR_MARGINAL_SINGLE ? 1 : desc->q;
+    if (q < 1 || q > CVAR_MAX_Q) return CVAR_ERR_PARAM;
+    if (desc->marginal == CVAR_MARGINAL_MIXTURE) {
+        if (!sigma_states) return CVAR_ERR_NULL;
+        for (int i = 0; i < 2 * q; ++i)
+            if (!(sigma_states[i] > 0.0) || !std::isfinite(sigma_states[i])) return CVAR_ERR_PARAM;
+    }
+    if (!(desc->w0 != 0.0) || !std::isfinite(desc->w0) || !std::isfinite(desc->w1)) return CVAR_ERR_PARAM;
+    if (desc->copula != CVAR_COPULA_PLACKETT && !(std::fabs(desc->rho) < 1.0)) return CVAR_ERR_PARAM;
+    if (desc->copula == CVAR_COPULA_STUDENT && !(desc->nu > 0.0 && std::isfinite(desc->nu))) return CVAR_ERR_PARAM;
+    if (desc->copula == CVAR_COPULA_PLACKETT && !(desc->theta > 0.0 && std::isfinite(desc->theta))) return CVAR_ERR_PARAM;
+    if (!(desc->tol > 0.0) || desc->max_iter < 0 || desc->max_iter > CVAR_MAX_ITER) return CVAR_ERR_PARAM;
+    if (!(desc->second_lo < desc->first_guess && desc->first_guess < desc->second_hi && desc->min_var < desc->second_lo &&
+          desc->second_hi < desc->max_var && desc->neg_inf < desc->min_var))
+        return CVAR_ERR_PARAM;
+
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
+        cudaGetLastError();
+        return CVAR_ERR_NO_DEVICE;
+    }
+    if (device < 0) {
+        if (cudaGetDevice(&device) != cudaSuccess) return CVAR_ERR_NO_DEVICE;
+    }
+    if (device >= ndev) return CVAR_ERR_NO_DEVICE;
+    DeviceGuard guard(device);
+    if (!guard.ok) return CVAR_ERR_NO_DEVICE;
+
+    cvar_plan* p = new (std::nothrow) cvar_plan();
+    if (!p) return (int)cudaErrorMemoryAllocation;
+    std::memset(p, 0, sizeof(*p));
+    p->desc = *desc;
+    p->desc.q = q;
+    p->device = device;
+
+    cudaDeviceProp prop;
+    int rc = (int)cudaGetDeviceProperties(&prop, device);
+    if (rc) { delete p; return rc; }
+    p->sm_count = prop.multiProcessorCount;
+    p->smem_bytes = smem_bytes_for(n);
+    if (p->smem_bytes > (size_t)prop.sharedMemPerBlockOptin) { delete p; return CVAR_ERR_SMEM; }
+
+    // ---- run constants -------------------------------------------------------------------
+    KernelParams& kp = p->kp;
+    std::memset(&kp, 0, sizeof(kp));
+    kp.copula = desc->copula;
+    kp.marginal = desc->marginal;
+    kp.n = n;
+    kp.q = q;
+    kp.compat = desc->compat_flags;
+    kp.rho = desc->rho; kp.nu = desc->nu; kp.theta = desc->theta;
+    kp.w0 = desc->w0; kp.w1 = desc->w1;
+    kp.neg_inf = desc->neg_inf; kp.first = desc->first_guess;
+    kp.second_lo = desc->second_lo; kp.second_hi = desc->second_hi;
+    kp.min_var = desc->min_var; kp.max_var = desc->max_var;
+    kp.cmin = (int)(std::upper_bound(x, x + n, desc->clip_lo) - x);
+    double dx_min = INFINITY;
+    for (int i = 1; i < n; ++i) dx_min = std::min(dx_min, x[i] - x[i - 1]);
+    kp.thick_width = 24.0 * dx_min;
+    const double LOG2E = 1.4426950408889634;
+    if (desc->copula == CVAR_COPULA_GAUSSIAN) {
+        const double om = 1.0 - desc->rho * desc->rho;
+        const double kappa = desc->rho * desc->rho / (2.0 * om);
+        kp.g_in_scale = std::sqrt(kappa * LOG2E);
+        kp.g_out_scale = (desc->rho < 0 ? -1.0 : 1.0) * std::sqrt(LOG2E / (2.0 * om));
+        kp.g_const = 1.0 / std::sqrt(om);
+    } else if (desc->copula == CVAR_COPULA_STUDENT) {
+        const double nu = desc->nu, om = 1.0 - desc->rho * desc->rho;
+        const double cs = 1.0 / std::sqrt(nu * om);
+        kp.g_in_scale = cs;
+        kp.g_out_scale = desc->rho * cs;
+        kp.g_const = std::exp(std::lgamma(0.5 * (nu + 2.0)) + std::lgamma(0.5 * nu) - 2.0 * std::lgamma(0.5 * (nu + 1.0))) /
+                     std::sqrt(om);
+        const double lbeta = std::lgamma(0.5 * nu) + std::lgamma(0.5) - std::lgamma(0.5 * nu + 0.5);
+        kp.tq_tail_lc = (-lbeta - 0.5 * std::log(nu)) + 0.5 * (nu - 1.0) * std::log(nu);
+    }
+    // iterations: every bracket's own requirement, and the largest of them is what the kernel records
+    FinalizeParams& fp = p->fp;
+    std::memset(&fp, 0, sizeof(fp));
+    const double blo[4] = {desc->min_var, desc->second_lo, desc->second_hi, desc->first_guess};
+    const double bhi[4] = {desc->second_lo, desc->first_guess, desc->max_var, desc->second_hi};
+    int need_max = 0;
+    for (int c = 0; c < 4; ++c) {
+        fp.lo[c] = blo[c];
+        fp.hi[c] = bhi[c];
+        fp.need[c] = needed_iterations(bhi[c] - blo[c], desc->tol);
+        need_max = std::max(need_max, fp.need[c]);
+    }
+    const int max_iter = desc->max_iter > 0 ? desc->max_iter : need_max;
+    if (max_iter > 28) { delete p; return CVAR_ERR_PARAM; }  // decision bits share a word with the bracket id
+    kp.max_iter = fp.max_iter = max_iter;
+    p->desc.max_iter = max_iter;
+
+#define PLAN_TRY(expr)                                   \
+    do {                                                 \
+        cudaError_t _e = (expr);                         \
+        if (_e != cudaSuccess) { cvar_plan_destroy(p); return (int)_e; } \
+    } while (0)
+
+    PLAN_TRY(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
+    PLAN_TRY(cudaEventCreate(&p->ev0));
+    PLAN_TRY(cudaEventCreate(&p->ev1));
+    PLAN_TRY(cudaMalloc(&p->d_x, sizeof(double) * n));
+    PLAN_TRY(cudaMalloc(&p->d_dx, sizeof(double) * n));
+    PLAN_TRY(cudaMalloc(&p->d_k, sizeof(int) * CVAR_MAX_ALPHA));
+    PLAN_TRY(cudaMemcpyAsync(p->d_x, x, sizeof(double) * n, cudaMemcpyHostToDevice, p->stream));
+    PLAN_TRY(cudaMemcpyAsync(p->d_dx, dx, sizeof(double) * n, cudaMemcpyHostToDevice, p->stream));
+    if (desc->marginal == CVAR_MARGINAL_MIXTURE) {
+        PLAN_TRY(cudaMalloc(&p->d_sigma_states, sizeof(double) * 2 * q));
+        PLAN_TRY(cudaMemcpyAsync(p->d_sigma_states, sigma_states, sizeof(double) * 2 * q, cudaMemcpyHostToDevice, p->stream));
+    }
+    kp.x = p->d_x;
+    kp.dx = p->d_dx;
+    kp.sigma_states = p->d_sigma_states;
+    if (desc->copula == CVAR_COPULA_STUDENT) {
+        PLAN_TRY(cudaMalloc(&p->d_tq_table, sizeof(double) * TQ_TABLE_DOUBLES));
+        tq_table_build_kernel<<<TQ_INTERVALS, 32, 0, p->stream>>>(desc->nu, p->d_tq_table);
+        PLAN_TRY(cudaGetLastError());
+        unsigned long long* d_err = nullptr;
+        PLAN_TRY(cudaMalloc(&d_err, sizeof(unsigned long long)));
+        PLAN_TRY(cudaMemsetAsync(d_err, 0, sizeof(unsigned long long), p->stream));
+        tq_table_check_kernel<<<TQ_INTERVALS, 32, 0, p->stream>>>(desc->nu, p->d_tq_table, kp.tq_tail_lc, d_err);
+        PLAN_TRY(cudaGetLastError());
+        unsigned long long bits = 0;
+        PLAN_TRY(cudaMemcpyAsync(&bits, d_err, sizeof(bits), cudaMemcpyDeviceToHost, p->stream));
+        PLAN_TRY(cudaStreamSynchronize(p->stream));
+        cudaFree(d_err);
+        std::memcpy(&p->tq_err, &bits, sizeof(double));
+        kp.tq_table = p->d_tq_table;
+    }
+    PLAN_TRY(cudaStreamSynchronize(p->stream));
+
+    // opt in to the dynamic shared memory this grid needs, for every instantiation
+    PLAN_TRY((cudaError_t)set_smem(solve_kernel<0>, p->smem_bytes));
+    PLAN_TRY((cudaError_t)set_smem(solve_kernel<1>, p->smem_bytes));
+    PLAN_TRY((cudaError_t)set_smem(solve_kernel<2>, p->smem_bytes));
+    PLAN_TRY((cudaError_t)set_smem(strip_mass_kernel<0>, p->smem_bytes));
+    PLAN_TRY((cudaError_t)set_smem(strip_mass_kernel<1>, p->smem_bytes));
+    PLAN_TRY((cudaError_t)set_smem(strip_mass_kernel<2>, p->smem_bytes));
+    int occ = 0;
+    switch (desc->copula) {
+        case CVAR_COPULA_GAUSSIAN: PLAN_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, solve_kernel<0>, CTA_THREADS, p->smem_bytes)); break;
+        case CVAR_COPULA_STUDENT: PLAN_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, solve_kernel<1>, CTA_THREADS, p->smem_bytes)); break;
+        default: PLAN_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, solve_kernel<2>, CTA_THREADS, p->smem_bytes));
+    }
+    p->ctas_per_sm = occ;
+#undef PLAN_TRY
+    *out = p;
+    return CVAR_OK;
+}
+
+int cvar_plan_destroy(cvar_plan_t* p) {
+    if (!p) return CVAR_OK;
+    DeviceGuard guard(p->device);
+    if (p->stream) cudaStreamSynchronize(p->stream);
+    cudaFree(p->d_x);
+    cudaFree(p->d_dx);
+    cudaFree(p->d_sigma_states);
+    cudaFree(p->d_tq_table);
+    cudaFree(p->d_ws);
+    cudaFree(p->d_k);
+    if (p->ev0) cudaEventDestroy(p->ev0);
+    if (p->ev1) cudaEventDestroy(p->ev1);
+    if (p->stream) cudaStreamDestroy(p->stream);
+    delete p;
+    return CVAR_OK;
+}
+
+int cvar_plan_get_info(const cvar_plan_t* p, cvar_plan_info_t* info) {
+    if (!p || !info) return CVAR_ERR_NULL;
+    info->device = p->device;
+    info->sm_count = p->sm_count;
+    info->max_iter = p->kp.max_iter;
+    info->ctas_per_sm = p->ctas_per_sm;
+    info->threads_per_cta = CTA_THREADS;
+    info->smem_bytes_per_cta = (int32_t)p->smem_bytes;
+    info->tq_table_max_rel_err = p->tq_err;
+    info->last_kernel_ms = p->last_kernel_ms;
+    return CVAR_OK;
+}
+
+// ---- strip masses ---------------------------------------------------------------------------
+int cvar_strip_mass_device(cvar_plan_t* p, const double* day_params, int64_t T, const double* bounds, double* out,
+                           uint64_t* out_cells, void* stream) {
+    if (!p || (T > 0 && (!day_params || !bounds || !out))) return CVAR_ERR_NULL;
+    if (T < 0 || T > 0x7fffffffLL) return CVAR_ERR_SIZE;
+    DeviceGuard guard(p->device);
+    return launch_strip(p, day_params, T, bounds, out, (unsigned long long*)out_cells, (cudaStream_t)stream);
+}
+
+int cvar_strip_mass_host(cvar_plan_t* p, const double* day_params, int64_t T, const double* bounds, double* out,
+                         uint64_t* out_cells) {
+    if (!p || (T > 0 && (!day_params || !bounds || !out))) return CVAR_ERR_NULL;
+    if (T < 0 || T > 0x7fffffffLL) return CVAR_ERR_SIZE;
+    if (T == 0) return CVAR_OK;
+    DeviceGuard guard(p->device);
+    const size_t b_day = align256(sizeof(double) * T * day_stride(p));
+    const size_t b_bnd = align256(sizeof(double) * T * 2);
+    const size_t b_out = align256(sizeof(double) * T);
+    const size_t b_cel = align256(sizeof(uint64_t) * T);
+    int rc = ensure_ws(p, b_day + b_bnd + b_out + b_cel);
+    if (rc) return rc;
+    char* ws = (char*)p->d_ws;
+    double* d_day = (double*)ws;
+    double* d_bnd = (double*)(ws + b_day);
+    double* d_out = (double*)(ws + b_day + b_bnd);
+    unsigned long long* d_cel = (unsigned long long*)(ws + b_day + b_bnd + b_out);
+    CU_TRY(cudaMemcpyAsync(d_day, day_params, sizeof(double) * T * day_stride(p), cudaMemcpyHostToDevice, p->stream));
+    CU_TRY(cudaMemcpyAsync(d_bnd, bounds, sizeof(double) * T * 2, cudaMemcpyHostToDevice, p->stream));
+    rc = launch_strip(p, d_day, T, d_bnd, d_out, out_cells ? d_cel : nullptr, p->stream);
+    if (rc) return rc;
+    CU_TRY(cudaMemcpyAsync(out, d_out, sizeof(double) * T, cudaMemcpyDeviceToHost, p->stream));
+    if (out_cells) CU_TRY(cudaMemcpyAsync(out_cells, d_cel, sizeof(uint64_t) * T, cudaMemcpyDeviceToHost, p->stream));
+    CU_TRY(cudaStreamSynchronize(p->stream));
+    return CVAR_OK;
+}
+
+// ---- solve ----------------------------------------------------------------------------------
+static int check_alphas(const double* alphas, int32_t n_alpha, AlphaSet* A) {
+    if (!alphas) return CVAR_ERR_NULL;
+    if (n_alpha < 1 || n_alpha > CVAR_MAX_ALPHA) return CVAR_ERR_SIZE;
+    A->n_alpha = n_alpha;
+    for (int i = 0; i < CVAR_MAX_ALPHA; ++i) A->a[i] = i < n_alpha ? alphas[i] : 0.0;
+    for (int i = 0; i < n_alpha; ++i)
+        if (!(alphas[i] > 0.0 && alphas[i] < 1.0)) return CVAR_ERR_PARAM;
+    return 0;
+}
+
+int cvar_solve_device(cvar_plan_t* p, const double* day_params, int64_t T, const double* alphas, int32_t n_alpha,
+                      uint32_t* traj, double* mass, uint64_t* cells, void* stream) {
+    if (!p || (T > 0 && (!day_params || !traj))) return CVAR_ERR_NULL;
+    if (T < 0 || T > 0x7fffffffLL) return CVAR_ERR_SIZE;
+    AlphaSet A;
+    int rc = check_alphas(alphas, n_alpha, &A);
+    if (rc) return rc;
+    DeviceGuard guard(p->device);
+    return launch_solve(p, day_params, T, A, traj, mass, (unsigned long long*)cells, (cudaStream_t)stream);
+}
+
+int cvar_finalize_device(cvar_plan_t* p, const uint32_t* traj, int64_t T, int32_t n_alpha, const int32_t* forced,
+                         double ptf_mean, double* var_out, int32_t* case_out, int32_t* iterations_out, void* stream) {
+    if (!p || (T > 0 && (!traj || !var_out))) return CVAR_ERR_NULL;
+    if (T < 0 || n_alpha < 1 || n_alpha > CVAR_MAX_ALPHA) return CVAR_ERR_SIZE;
+    if (forced)
+        for (int i = 0; i < n_alpha; ++i)
+            if (forced[i] > p->kp.max_iter) return CVAR_ERR_PARAM;
+    DeviceGuard guard(p->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = launch_finalize(p, traj, T, n_alpha, forced, ptf_mean, var_out, case_out, st);
+    if (rc) return rc;
+    if (iterations_out)
+        CU_TRY(cudaMemcpyAsync(iterations_out, p->d_k, sizeof(int) * n_alpha, cudaMemcpyDeviceToDevice, st));
+    return CVAR_OK;
+}
+
+int cvar_solve_host(cvar_plan_t* p, const double* day_params, int64_t T, const double* alphas, int32_t n_alpha,
+                    const int32_t* forced, double ptf_mean, double* var_out, int32_t* case_out, uint64_t* cells_out,
+                    int32_t* iterations_out) {
+    if (!p || (T > 0 && (!day_params || !var_out))) return CVAR_ERR_NULL;
+    if (T < 0 || T > 0x7fffffffLL) return CVAR_ERR_SIZE;
+    AlphaSet A;
+    int rc = check_alphas(alphas, n_alpha, &A);
+    if (rc) return rc;
+    if (forced)
+        for (int i = 0; i < n_alpha; ++i)
+            if (forced[i] > p->kp.max_iter) return CVAR_ERR_PARAM;
+    DeviceGuard guard(p->device);
+    const size_t na = (size_t)n_alpha;
+    const size_t b_day = align256(sizeof(double) * T * day_stride(p));
+    const size_t b_trj = align256(sizeof(uint32_t) * 2 * T * na);
+    const size_t b_var = align256(sizeof(double) * T * na);
+    const size_t b_cas = align256(sizeof(int32_t) * T * na);
+    const size_t b_cel = align256(sizeof(uint64_t) * T * na);
+    rc = ensure_ws(p, b_day + b_trj + b_var + b_cas + b_cel);
+    if (rc) return rc;
+    char* ws = (char*)p->d_ws;
+    double* d_day = (double*)ws;
+    uint32_t* d_trj = (uint32_t*)(ws + b_day);
+    double* d_var = (double*)(ws + b_day + b_trj);
+    int32_t* d_cas = (int32_t*)(ws + b_day + b_trj + b_var);
+    unsigned long long* d_cel = (unsigned long long*)(ws + b_day + b_trj + b_var + b_cas);
+    if (T > 0) CU_TRY(cudaMemcpyAsync(d_day, day_params, sizeof(double) * T * day_stride(p), cudaMemcpyHostToDevice, p->stream));
+    CU_TRY(cudaEventRecord(p->ev0, p->stream));
+    rc = launch_solve(p, d_day, T, A, d_trj, nullptr, cells_out ? d_cel : nullptr, p->stream);
+    if (rc) return rc;
+    rc = launch_finalize(p, d_trj, T, n_alpha, forced, ptf_mean, d_var, case_out ? d_cas : nullptr, p->stream);
+    if (rc) return rc;
+    CU_TRY(cudaEventRecord(p->ev1, p->stream));
+    if (T > 0) {
+        CU_TRY(cudaMemcpyAsync(var_out, d_var, sizeof(double) * T * na, cudaMemcpyDeviceToHost, p->stream));
+        if (case_out) CU_TRY(cudaMemcpyAsync(case_out, d_cas, sizeof(int32_t) * T * na, cudaMemcpyDeviceToHost, p->stream));
+        if (cells_out) CU_TRY(cudaMemcpyAsync(cells_out, d_cel, sizeof(uint64_t) * T * na, cudaMemcpyDeviceToHost, p->stream));
+    }
+    if (iterations_out) CU_TRY(cudaMemcpyAsync(iterations_out, p->d_k, sizeof(int) * n_alpha, cudaMemcpyDeviceToHost, p->stream));
+    CU_TRY(cudaStreamSynchronize(p->stream));
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, p->ev0, p->ev1) == cudaSuccess) p->last_kernel_ms = ms;
+    return CVAR_OK;
+}
+
+// ---- special functions (tests) ---------------------------------------------------------------
+int cvar_test_special_host(cvar_plan_t* p, int32_t which, const double* in, int64_t count, double* out) {
+    if (!p || (count > 0 && (!in || !out))) return CVAR_ERR_NULL;
+    if (count < 0) return CVAR_ERR_SIZE;
+    if (count == 0) return CVAR_OK;
+    if ((which == 0 || which == 1) && p->desc.copula != CVAR_COPULA_STUDENT) return CVAR_ERR_COPULA;
+    DeviceGuard guard(p->device);
+    const size_t b = align256(sizeof(double) * count);
+    int rc = ensure_ws(p, 2 * b);
+    if (rc) return rc;
+    double* d_in = (double*)p->d_ws;
+    double* d_out = (double*)((char*)p->d_ws + b);
+    CU_TRY(cudaMemcpyAsync(d_in, in, sizeof(double) * count, cudaMemcpyHostToDevice, p->stream));
+    special_kernel<<<(unsigned)((count + 127) / 128), 128, 0, p->stream>>>(which, p->desc.nu, p->d_tq_table, p->kp.tq_tail_lc,
+                                                                          d_in, (long long)count, d_out);
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaMemcpyAsync(out, d_out, sizeof(double) * count, cudaMemcpyDeviceToHost, p->stream));
+    CU_TRY(cudaStreamSynchronize(p->stream));
+    return CVAR_OK;
+}
+
+// ---- elementwise copula density ----------------------------------------------------------------
+int cvar_copula_density_host(int32_t copula, double rho, double nu, double theta, const double* u, int64_t count,
+                             double* out, int device) {
+    if (count > 0 && (!u || !out)) return CVAR_ERR_NULL;
+    if (count < 0) return CVAR_ERR_SIZE;
+    if (copula < 0 || copula > 2) return CVAR_ERR_COPULA;
+    if (copula != CVAR_COPULA_PLACKETT && !(std::fabs(rho) < 1.0)) return CVAR_ERR_PARAM;
+    if (copula == CVAR_COPULA_STUDENT && !(nu > 0.0)) return CVAR_ERR_PARAM;
+    if (copula == CVAR_COPULA_PLACKETT && !(theta > 0.0)) return CVAR_ERR_PARAM;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
+        cudaGetLastError();
+        return CVAR_ERR_NO_DEVICE;
+    }
+    if (device < 0 && cudaGetDevice(&device) != cudaSuccess) return CVAR_ERR_NO_DEVICE;
+    if (device >= ndev) return CVAR_ERR_NO_DEVICE;
+    if (count == 0) return CVAR_OK;
+    DeviceGuard guard(device);
+    double kc = 0.0;
+    if (copula == CVAR_COPULA_STUDENT)
+        kc = std::exp(std::lgamma(0.5 * (nu + 2.0)) + std::lgamma(0.5 * nu) - 2.0 * std::lgamma(0.5 * (nu + 1.0))) /
+             std::sqrt(1.0 - rho * rho);
+    double *d_u = nullptr, *d_o = nullptr;
+    CU_TRY(cudaMalloc(&d_u, sizeof(double) * 2 * count));
+    cudaError_t e = cudaMalloc(&d_o, sizeof(double) * count);
+    if (e != cudaSuccess) { cudaFree(d_u); return (int)e; }
+    e = cudaMemcpy(d_u, u, sizeof(double) * 2 * count, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        copula_density_kernel<<<(unsigned)((count + 127) / 128), 128>>>(copula, rho, nu, theta, kc, d_u, (long long)count, d_o);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpy(out, d_o, sizeof(double) * count, cudaMemcpyDeviceToHost);
+    cudaFree(d_u);
+    cudaFree(d_o);
+    return (int)e;
+}
+
+}  // extern "C"

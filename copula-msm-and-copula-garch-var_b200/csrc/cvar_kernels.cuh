@@ -1,0 +1,644 @@
+// cvar_kernels.cuh -- the per-day VaR solve on sm_100a.
+//
+// One CTA per out-of-sample day.  The CTA
+//   stage 0  evaluates every per-axis-point quantity once (marginal cdf/pdf, the MSM mixture over its
+//            q states, the copula quantile) and leaves them in shared memory in the form the cell loop
+//            wants (reference: integration_functions/*_integration_function.py,
+//            copulas/*/*.py),
+//   then, for every alpha, runs the reference's whole bracket + bisection state machine in-kernel
+//   (utils/calc_var_class.py:95-177, 250-309): each step integrates only the strip between the previous
+//   and the new boundary (create_grids.py:102-110), with FP64 warp-shuffle + block reductions, and no
+//   host round trip per iteration.
+//
+// Cell membership is decided by the reference's exact expression  x[j] <= (q - x[i]*w1)/w0  evaluated
+// with individually rounded operations (integration_algo.py:20), so the set of cells in every strip is
+// identical to the reference's; only the cell *weights* are computed in a restructured (per-axis
+// factored) form.
+#pragma once
+#include "cvar_math.cuh"
+
+namespace cvar {
+
+constexpr int CTA_THREADS = 256;
+constexpr int CTA_WARPS = CTA_THREADS / 32;
+constexpr int ROWS_PER_GROUP = 4;  // adjacent outer rows sharing one pass over the inner axis (THICK mode)
+
+typedef unsigned short u16;
+
+struct KernelParams {
+    int copula, marginal, n, q;
+    unsigned compat;
+    int max_iter;
+    int cmin;  // #{x <= clip_lo}: first inner index that can ever belong to a strip
+    double rho, nu, theta, w0, w1;
+    double neg_inf, first, second_lo, second_hi, min_var, max_var;
+    double thick_width;  // strips at least this wide (in units of the inner coordinate) use warp-per-row-group
+    // copula constants prepared on the host
+    double g_in_scale;   // gaussian: sqrt(kappa*log2e)          student: 1/sqrt(nu(1-rho^2))
+    double g_out_scale;  // gaussian: sgn(rho) sqrt(log2e/(2(1-rho^2)))   student: rho/sqrt(nu(1-rho^2))
+    double g_const;      // gaussian: (1-rho^2)^(-1/2)            student: Gamma-ratio / sqrt(1-rho^2)
+    double tq_tail_lc;   // student: log of the leading tail coefficient
+    const double* x;
+    const double* dx;
+    const double* sigma_states;  // [2][q] or nullptr
+    const double* tq_table;      // student only
+};
+
+struct AlphaSet {
+    int n_alpha;
+    double a[8];
+};
+
+// dynamic shared memory carve-up
+struct Smem {
+    double* xs;     // [n] axis (membership searches)
+    double* in0;    // [n] inner-axis array 0
+    double* in1;    // [n] inner-axis array 1
+    double* out0;   // [n] outer-axis array 0
+    double* out1;   // [n]
+    double* out2;   // [n]
+    u16* c[3];      // [n] each: inner index bounds per outer row
+    double* red;    // [2][CTA_WARPS]
+    unsigned* redc; // [2][CTA_WARPS]
+    int* live;      // [4]: dead-prefix / dead-suffix counts per axis
+};
+
+__host__ __device__ inline size_t smem_bytes_for(int n) {
+    size_t npad = (size_t)((n + 3) & ~3);
+    return npad * 8 * 6 + npad * 2 * 3 + 2 * CTA_WARPS * 8 + 2 * CTA_WARPS * 4 + 16 + 64;
+}
+
+__device__ __forceinline__ Smem carve(unsigned char* base, int n) {
+    size_t npad = (size_t)((n + 3) & ~3);
+    Smem S;
+    double* d = reinterpret_cast<double*>(base);
+    S.xs = d;
+    S.in0 = d + npad;
+    S.in1 = d + 2 * npad;
+    S.out0 = d + 3 * npad;
+    S.out1 = d + 4 * npad;
+    S.out2 = d + 5 * npad;
+    S.red = d + 6 * npad;
+    u16* h = reinterpret_cast<u16*>(S.red + 2 * CTA_WARPS);
+    S.c[0] = h;
+    S.c[1] = h + npad;
+    S.c[2] = h + 2 * npad;
+    S.redc = reinterpret_cast<unsigned*>(h + 3 * npad);
+    S.live = reinterpret_cast<int*>(S.redc + 2 * CTA_WARPS);
+    return S;
+}
+
+// ---------------------------------------------------------------------------------------------
+// stage 0: per-axis quantities
+// ---------------------------------------------------------------------------------------------
+template <int COPULA>
+__device__ void stage0(const KernelParams& P, const double* __restrict__ dayp, const Smem& S) {
+    const int n = P.n, q = P.q;
+    if (threadIdx.x < 4) S.live[threadIdx.x] = 0;
+    __syncthreads();
+    const bool swap = (P.compat & 1u) != 0;
+    for (int i = threadIdx.x; i < n; i += CTA_THREADS) {
+        const double xi = P.x[i], dxi = P.dx[i];
+        S.xs[i] = xi;
+        double u[2], a[2];
+        if (P.marginal == 0) {
+            // garch_integration_function.py:27-38  (u = Phi(x/sigma), pdf = phi(x/sigma)/sigma)
+#pragma unroll
+            for (int d = 0; d < 2; ++d) {
+                const double sg = dayp[d];
+                const double z = __ddiv_rn(xi, sg);
+                u[d] = phi_via_erf(z);
+                a[d] = (CVAR_INV_SQRT_2PI * exp(-0.5 * z * z) / sg) * dxi;
+            }
+        } else {
+            // msm_integration_function.py:32-36 (cdf mixture) and create_grids.py:121,143 (pdf mixture
+            // with the vol states of the OTHER asset when the Q3 compat bit is set)
+#pragma unroll
+            for (int d = 0; d < 2; ++d) {
+                double su = 0.0, sa = 0.0;
+                const double* pr = dayp + d * q;
+                const double* sg_own = P.sigma_states + d * q;
+                const double* sg_pdf = P.sigma_states + (swap ? (1 - d) : d) * q;
+                for (int s = 0; s < q; ++s) {
+                    const double p = pr[s];
+                    su += p * phi_via_erf(__ddiv_rn(xi, sg_own[s]));
+                    const double zz = __ddiv_rn(xi, sg_pdf[s]);
+                    sa += p * (exp(-0.5 * zz * zz) / (2.5066282746310002 * sg_pdf[s]));
+                }
+                u[d] = su;
+                a[d] = dxi * sa;
+            }
+        }
+        if (COPULA == 2) {
+            S.in0[i] = u[1];
+            S.in1[i] = a[1];
+            S.out0[i] = u[0];
+            S.out1[i] = a[0];
+        } else {
+            double y[2];
+#pragma unroll
+            for (int d = 0; d < 2; ++d) {
+                if (COPULA == 0)
+                    y[d] = normcdfinv(u[d]);
+                else
+                    y[d] = t_quantile_table(P.tq_table, P.nu, P.tq_tail_lc, u[d]);
+                if (!isfinite(y[d])) {  // u == 0 or u == 1: the reference's density is NaN there (Q5/Q10)
+                    atomicAdd(&S.live[2 * d + (y[d] < 0.0 ? 0 : 1)], 1);
+                    y[d] = 0.0;
+                    a[d] = 0.0;
+                }
+            }
+            const double l1 = fmax(log2(a[1]), -1100.0);
+            if (COPULA == 0) {
+                S.in0[i] = P.g_in_scale * y[1];
+                S.in1[i] = l1;
+                S.out0[i] = P.g_out_scale * y[0];
+                S.out1[i] = a[0] * P.g_const * exp(0.5 * y[0] * y[0]);
+            } else {
+                const double hp = 0.5 * (P.nu + 1.0);
+                const double c1 = 1.0 + y[1] * y[1] / P.nu;
+                const double c0 = 1.0 + y[0] * y[0] / P.nu;
+                S.in0[i] = P.g_in_scale * y[1];
+                S.in1[i] = fmax(l1 + hp * log2(c1), -1100.0);
+                S.out0[i] = P.g_out_scale * y[0];
+                S.out1[i] = c0;
+                S.out2[i] = a[0] * P.g_const * exp2(hp * log2(c0));
+            }
+        }
+    }
+    __syncthreads();
+}
+
+// ---------------------------------------------------------------------------------------------
+// membership: #{ j : x[j] <= g } by binary search inside [lo, hi]
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double inner_bound(double q, double xi, double w0, double w1) {
+    // (q - x_outer * w[1]) / w[0], every operation individually rounded (integration_algo.py:20)
+    return __ddiv_rn(__dsub_rn(q, __dmul_rn(xi, w1)), w0);
+}
+
+__device__ __forceinline__ int count_le(const double* __restrict__ xs, double g, int lo, int hi) {
+    while (lo < hi) {
+        int mid = (lo + hi) >> 1;
+        if (xs[mid] <= g)
+            lo = mid + 1;
+        else
+            hi = mid;
+    }
+    return lo;
+}
+
+// ctarget[i] = max(#{x <= g_i(q)}, cmin) for every outer row; the search is confined to [slo[i], shi[i]]
+__device__ __forceinline__ void count_rows(const KernelParams& P, const Smem& S, double q, u16* ctarget,
+                                           const u16* slo, const u16* shi) {
+    const int n = P.n;
+    for (int i = threadIdx.x; i < n; i += CTA_THREADS) {
+        const double g = inner_bound(q, S.xs[i], P.w0, P.w1);
+        int lo = slo ? (int)slo[i] : 0;
+        int hi = shi ? (int)shi[i] : n;
+        if (lo > 0 && !(S.xs[lo - 1] <= g)) lo = 0;  // stored bounds are clipped at cmin; stay exact
+        int c = count_le(S.xs, g, lo, hi);
+        ctarget[i] = (u16)max(c, P.cmin);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// cell weights
+// ---------------------------------------------------------------------------------------------
+template <int COPULA>
+struct Row;  // per-outer-row constants held in registers
+
+template <>
+struct Row<0> {  // Gaussian:  W = rowfac * 2^( l1[j] - (y1'[j] - m0)^2 )
+    double m0, fac;
+    __device__ __forceinline__ void load(const KernelParams&, const Smem& S, int i) {
+        m0 = S.out0[i];
+        fac = S.out1[i];
+    }
+    __device__ __forceinline__ double cell(const KernelParams&, double a, double b) const {
+        const double d = a - m0;
+        return exp2_fast(fma(-d, d, b));
+    }
+};
+
+template <>
+struct Row<1> {  // Student-t: W = rowfac * 2^( l1[j] - (nu+2)/2 * log2( c0 + (y1'[j] - m0)^2 ) )
+    double m0, c0, fac;
+    __device__ __forceinline__ void load(const KernelParams&, const Smem& S, int i) {
+        m0 = S.out0[i];
+        c0 = S.out1[i];
+        fac = S.out2[i];
+    }
+    __device__ __forceinline__ double cell(const KernelParams& P, double a, double b) const {
+        const double d = a - m0;
+        const double t = fma(d, d, c0);
+        return exp2_fast(fma(-0.5 * (P.nu + 2.0), log2_fast(t), b));
+    }
+};
+
+template <>
+struct Row<2> {  // Plackett (the reference's formula, plackett.py:66-69), u = row, v = column
+    double n0, n1, p0, r0, eta, fac;
+    __device__ __forceinline__ void load(const KernelParams& P, const Smem& S, int i) {
+        const double u = S.out0[i];
+        eta = P.theta - 1.0;
+        p0 = 1.0 + eta * u;
+        r0 = 1.0 + eta * (1.0 - u);
+        n0 = P.theta * p0;
+        n1 = P.theta * eta * (1.0 - 2.0 * u);
+        fac = S.out1[i];
+    }
+    __device__ __forceinline__ double cell(const KernelParams&, double v, double a1) const {
+        const double num = fma(n1, v, n0);
+        const double pp = fma(eta, v, p0);
+        const double rr = fma(-eta, v, r0);
+        const double dd = pp * rr;
+        return (a1 * num) * rcp_fast(dd * dd);
+    }
+};
+
+struct StripResult {
+    double mass;
+    unsigned cells;
+    bool poisoned;
+};
+
+struct Live {  // live window of rows / columns (cells outside have an infinite copula quantile)
+    int i_lo, i_hi, j_lo, j_hi;
+};
+
+// block-wide deterministic sum; every thread receives the same value
+__device__ __forceinline__ StripResult block_reduce(const Smem& S, int& parity, double v, unsigned cells, bool poison) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    cells = __reduce_add_sync(0xffffffffu, cells);
+    if (lane == 0) {
+        S.red[parity * CTA_WARPS + warp] = v;
+        S.redc[parity * CTA_WARPS + warp] = cells;
+    }
+    const int anyp = __syncthreads_or(poison ? 1 : 0);
+    StripResult r;
+    r.mass = 0.0;
+    r.cells = 0;
+#pragma unroll
+    for (int w = 0; w < CTA_WARPS; ++w) {
+        r.mass += S.red[parity * CTA_WARPS + w];
+        r.cells += S.redc[parity * CTA_WARPS + w];
+    }
+    r.poisoned = anyp != 0;
+    parity ^= 1;
+    return r;
+}
+
+// Sum of the cell weights with inner index in [ca[i], cb[i]) for every outer row i (ca == nullptr: cmin).
+// THICK: a warp walks ROWS_PER_GROUP adjacent rows with its lanes across the inner axis.
+// THIN : one thread per row (strips a few cells wide).
+template <int COPULA>
+__device__ StripResult strip_sum(const KernelParams& P, const Smem& S, const Live& L, int& parity, const u16* ca,
+                                 const u16* cb, bool thick, bool poison_mode) {
+    const int n = P.n;
+    double total = 0.0;
+    unsigned cells = 0;
+    bool poison = false;
+    if (thick) {
+        __syncthreads();  // bounds were written one thread per row
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        const int ngroups = (n + ROWS_PER_GROUP - 1) / ROWS_PER_GROUP;
+        for (int grp = warp; grp < ngroups; grp += CTA_WARPS) {
+            const int i0 = grp * ROWS_PER_GROUP;
+            int js[ROWS_PER_GROUP], je[ROWS_PER_GROUP];
+            int jmin = 0x7fffffff, jmax = 0;
+#pragma unroll
+            for (int r = 0; r < ROWS_PER_GROUP; ++r) {
+                const int i = i0 + r;
+                int s = 0, e = 0;
+                if (i < n) {
+                    s = ca ? (int)ca[i] : P.cmin;
+                    e = (int)cb[i];
+                    if (e > s) {
+                        if (lane == 0) cells += (unsigned)(e - s);
+                        if (i < L.i_lo || i >= L.i_hi) {
+                            poison = true;
+                            e = s;
+                        } else {
+                            if (s < L.j_lo || e > L.j_hi) poison = true;
+                            s = max(s, L.j_lo);
+                            e = min(e, L.j_hi);
+                        }
+                    }
+                    if (e <= s) s = e = 0;
+                }
+                js[r] = s;
+                je[r] = e;
+                if (e > s) {
+                    jmin = min(jmin, s);
+                    jmax = max(jmax, e);
+                }
+            }
+            if (jmin >= jmax) continue;
+            Row<COPULA> row[ROWS_PER_GROUP];
+            double acc[ROWS_PER_GROUP];
+#pragma unroll
+            for (int r = 0; r < ROWS_PER_GROUP; ++r) {
+                row[r].load(P, S, min(i0 + r, n - 1));
+                acc[r] = 0.0;
+            }
+            for (int j = jmin + lane; j < jmax; j += 32) {
+                const double a = S.in0[j], b = S.in1[j];
+#pragma unroll
+                for (int r = 0; r < ROWS_PER_GROUP; ++r) {
+                    const double w = row[r].cell(P, a, b);
+                    if (j >= js[r] && j < je[r]) acc[r] += w;
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < ROWS_PER_GROUP; ++r) total = fma(row[r].fac, acc[r], total);
+        }
+    } else {
+        for (int i = threadIdx.x; i < n; i += CTA_THREADS) {
+            int s = ca ? (int)ca[i] : P.cmin;
+            int e = (int)cb[i];
+            if (e <= s) continue;
+            cells += (unsigned)(e - s);
+            if (i < L.i_lo || i >= L.i_hi) {
+                poison = true;
+                continue;
+            }
+            if (s < L.j_lo || e > L.j_hi) poison = true;
+            s = max(s, L.j_lo);
+            e = min(e, L.j_hi);
+            if (e <= s) continue;
+            Row<COPULA> row;
+            row.load(P, S, i);
+            double acc = 0.0;
+            for (int j = s; j < e; ++j) acc += row.cell(P, S.in0[j], S.in1[j]);
+            total = fma(row.fac, acc, total);
+        }
+    }
+    StripResult r = block_reduce(S, parity, total, cells, poison && poison_mode);
+    if (r.poisoned) r.mass = NAN;
+    return r;
+}
+
+__device__ __forceinline__ bool is_thick(const KernelParams& P, double a, double b) {
+    return fabs((b - a) / P.w0) >= P.thick_width;
+}
+
+// ---------------------------------------------------------------------------------------------
+// the solve kernel
+// ---------------------------------------------------------------------------------------------
+template <int COPULA>
+__global__ void __launch_bounds__(CTA_THREADS, 2)
+solve_kernel(KernelParams P, const double* __restrict__ day_params, long long T, AlphaSet A,
+             unsigned* __restrict__ traj, double* __restrict__ mass_out, unsigned long long* __restrict__ cells_out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const Smem S = carve(smem_raw, P.n);
+    const long long day = blockIdx.x;
+    const int stride = (P.marginal == 0) ? 2 : 2 * P.q;
+    stage0<COPULA>(P, day_params + day * stride, S);
+
+    Live L;
+    if (COPULA == 2) {
+        L.i_lo = 0; L.i_hi = P.n; L.j_lo = 0; L.j_hi = P.n;
+    } else {
+        L.i_lo = S.live[0]; L.i_hi = P.n - S.live[1];
+        L.j_lo = S.live[2]; L.j_hi = P.n - S.live[3];
+    }
+    // Q5: NaN cells are zeroed on the single-normal path, poison the strip on the mixture path
+    const bool poison_mode = (COPULA != 2) && (P.marginal == 1) && ((P.compat & 4u) != 0);
+    int parity = 0;
+
+    bool have_f3 = false;
+    StripResult f3 = {0.0, 0u, false};
+
+    for (int ia = 0; ia < A.n_alpha; ++ia) {
+        const double alpha = A.a[ia];
+        unsigned long long ncell = 0;
+        // --- probe 1: F(first)  (calc_var_class.py:114-119)
+        count_rows(P, S, P.first, S.c[0], nullptr, nullptr);
+        if (!have_f3) {
+            f3 = strip_sum<COPULA>(P, S, L, parity, nullptr, S.c[0], true, poison_mode);
+            have_f3 = true;
+        } else {
+            __syncthreads();
+        }
+        ncell += f3.cells;
+        // --- probe 2  (:125-142)
+        double lo2, hi2;
+        if (f3.mass >= alpha) { lo2 = P.second_lo; hi2 = P.first; } else { lo2 = P.first; hi2 = P.second_hi; }
+        double prev_upper = (lo2 == P.second_lo) ? P.second_lo : P.first;  // Q6
+        const u16 *pa, *pb;
+        if (lo2 == P.first) {
+            count_rows(P, S, hi2, S.c[1], S.c[0], nullptr);
+            pa = S.c[0]; pb = S.c[1];
+        } else {
+            count_rows(P, S, lo2, S.c[1], nullptr, S.c[0]);
+            pa = S.c[1]; pb = S.c[0];
+        }
+        const StripResult s2 = strip_sum<COPULA>(P, S, L, parity, pa, pb, is_thick(P, lo2, hi2), poison_mode);
+        ncell += s2.cells;
+        double R = (lo2 == P.first) ? f3.mass + s2.mass : f3.mass - s2.mass;
+        if ((P.compat & 2u) == 0 && lo2 == P.first) prev_upper = hi2;  // intended behaviour: R = F(hi2)
+        // --- bracket  (:147-155)
+        int kase;
+        double lo, hi;
+        u16 *cl, *ch, *cm;
+        if (R > alpha && hi2 == P.second_hi) {
+            kase = 3; lo = P.first; hi = P.second_hi; cl = S.c[0]; ch = S.c[1]; cm = S.c[2];
+        } else if (R > alpha) {
+            kase = 0; lo = P.min_var; hi = P.second_lo; ch = S.c[1]; cl = S.c[2]; cm = S.c[0];
+            count_rows(P, S, lo, cl, nullptr, ch);
+        } else if (R < alpha && hi2 == P.first) {
+            kase = 1; lo = P.second_lo; hi = P.first; cl = S.c[1]; ch = S.c[0]; cm = S.c[2];
+        } else if (R < alpha && hi2 == P.second_hi) {
+            kase = 2; lo = P.second_hi; hi = P.max_var; cl = S.c[1]; ch = S.c[2]; cm = S.c[0];
+            count_rows(P, S, hi, ch, cl, nullptr);
+        } else {
+            kase = 4; lo = hi = NAN; cl = ch = cm = S.c[0];
+        }
+        bool stack = !(hi == P.second_lo || hi == P.second_hi);  // :160
+        unsigned dec = 0, zer = 0;
+        if (kase != 4) {
+            for (int k = 0; k < P.max_iter; ++k) {
+                const double mid = (lo + hi) / 2;
+                const double a = stack ? lo : mid, b = stack ? mid : hi;
+                count_rows(P, S, mid, cm, cl, ch);
+                const StripResult s = strip_sum<COPULA>(P, S, L, parity, stack ? cl : cm, stack ? cm : ch,
+                                                        is_thick(P, a, b), poison_mode);
+                ncell += s.cells;
+                R = (a == prev_upper) ? R + s.mass : R - s.mass;  // adjust_integral (:241-246)
+                if (R == 0.0) zer |= 1u << k;
+                stack = R < alpha;                                 // :298
+                if (stack) { dec |= 1u << k; lo = mid; u16* t = cl; cl = cm; cm = t; }
+                else       { hi = mid;       u16* t = ch; ch = cm; cm = t; }
+                prev_upper = mid;
+            }
+        }
+        if (threadIdx.x == 0) {
+            const long long o = (long long)ia * T + day;
+            traj[2 * o] = dec | ((unsigned)kase << 28);
+            traj[2 * o + 1] = zer;
+            if (mass_out) mass_out[o] = R;
+            if (cells_out) cells_out[o] = ncell;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// strip-mass kernel (parity seam for compute_integral)
+// ---------------------------------------------------------------------------------------------
+template <int COPULA>
+__global__ void __launch_bounds__(CTA_THREADS, 2)
+strip_mass_kernel(KernelParams P, const double* __restrict__ day_params, const double* __restrict__ bounds,
+                  double* __restrict__ out, unsigned long long* __restrict__ cells_out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const Smem S = carve(smem_raw, P.n);
+    const long long day = blockIdx.x;
+    const int stride = (P.marginal == 0) ? 2 : 2 * P.q;
+    stage0<COPULA>(P, day_params + day * stride, S);
+    Live L;
+    if (COPULA == 2) {
+        L.i_lo = 0; L.i_hi = P.n; L.j_lo = 0; L.j_hi = P.n;
+    } else {
+        L.i_lo = S.live[0]; L.i_hi = P.n - S.live[1];
+        L.j_lo = S.live[2]; L.j_hi = P.n - S.live[3];
+    }
+    const bool poison_mode = (COPULA != 2) && (P.marginal == 1) && ((P.compat & 4u) != 0);
+    int parity = 0;
+    const double lo = bounds[2 * day], hi = bounds[2 * day + 1];
+    count_rows(P, S, lo, S.c[0], nullptr, nullptr);
+    count_rows(P, S, hi, S.c[1], nullptr, nullptr);
+    // an inverted pair yields an empty strip (cb <= ca), like the reference's empty np.where
+    const StripResult s = strip_sum<COPULA>(P, S, L, parity, S.c[0], S.c[1], true, poison_mode);
+    if (threadIdx.x == 0) {
+        out[day] = s.mass;
+        if (cells_out) cells_out[day] = s.cells;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// finalize: global iteration count (Q7) and VaR reconstruction
+// ---------------------------------------------------------------------------------------------
+struct FinalizeParams {
+    int max_iter;
+    int need[4];  // iterations each bracket needs to reach the tolerance (A, B, C, D)
+    double lo[4], hi[4];
+    double ptf_mean;
+    int forced[8];  // < 0: derive
+};
+
+// one block per alpha: K = min( max_d need[case_d], first k at which every day's mass was exactly 0 )
+__global__ void finalize_reduce_kernel(FinalizeParams F, const unsigned* __restrict__ traj, long long T,
+                                       int* __restrict__ k_out) {
+    __shared__ int s_need;
+    __shared__ unsigned s_nonzero;
+    const int ia = blockIdx.x;
+    if (threadIdx.x == 0) {
+        s_need = 0;
+        s_nonzero = 0;
+    }
+    __syncthreads();
+    int need = 0;
+    unsigned nonzero = 0;
+    const unsigned mask = (F.max_iter >= 32) ? 0xffffffffu : ((1u << F.max_iter) - 1u);
+    for (long long d = threadIdx.x; d < T; d += blockDim.x) {
+        const unsigned w0 = traj[2 * (ia * T + d)], w1 = traj[2 * (ia * T + d) + 1];
+        const unsigned kase = (w0 >> 28) & 7u;
+        if (kase < 4) {
+            need = max(need, F.need[kase]);
+            nonzero |= (~w1) & mask;
+        } else {
+            nonzero |= mask;  // NaN mass is never == 0
+        }
+    }
+    atomicMax(&s_need, need);
+    atomicOr(&s_nonzero, nonzero);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int K = s_need;
+        const unsigned allzero = (~s_nonzero) & mask;
+        if (T > 0 && allzero) K = min(K, __ffs(allzero) - 1);
+        if (F.forced[ia] >= 0) K = F.forced[ia];
+        k_out[ia] = min(K, F.max_iter);
+    }
+}
+
+__global__ void finalize_apply_kernel(FinalizeParams F, const unsigned* __restrict__ traj, long long T, int n_alpha,
+                                      const int* __restrict__ k_in, double* __restrict__ var_out,
+                                      int* __restrict__ case_out) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= T * n_alpha) return;
+    const int ia = (int)(idx / T);
+    const unsigned w0 = traj[2 * idx];
+    const unsigned kase = (w0 >> 28) & 7u;
+    double v = NAN;
+    if (kase < 4) {
+        double lo = F.lo[kase], hi = F.hi[kase];
+        const int K = k_in[ia];
+        for (int k = 0; k < K; ++k) {
+            const double mid = (lo + hi) / 2;
+            if ((w0 >> k) & 1u) lo = mid; else hi = mid;
+        }
+        v = (lo + hi) / 2 + F.ptf_mean;
+    }
+    var_out[idx] = v;
+    if (case_out) case_out[idx] = (int)kase;
+}
+
+// ---------------------------------------------------------------------------------------------
+// special-function test kernel
+// ---------------------------------------------------------------------------------------------
+__global__ void special_kernel(int which, double nu, const double* __restrict__ table, double tail_lc,
+                               const double* __restrict__ in, long long count, double* __restrict__ out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const double v = in[i];
+    double r;
+    switch (which) {
+        case 0: r = t_quantile_table(table, nu, tail_lc, v); break;
+        case 1: { TDist D = tdist_make(nu); r = t_quantile_iterative(D, v); break; }
+        case 2: r = exp2_fast(v); break;
+        case 3: r = log2_fast(v); break;
+        case 4: r = phi_via_erf(v); break;
+        case 5: r = normcdfinv(v); break;
+        case 6: r = rcp_fast(v); break;
+        default: r = NAN;
+    }
+    out[i] = r;
+}
+
+// ---------------------------------------------------------------------------------------------
+// elementwise copula density c(u0, u1) (the calculators' `copula_density` hook; not on the solve path)
+// ---------------------------------------------------------------------------------------------
+__global__ void copula_density_kernel(int copula, double rho, double nu, double theta, double kc,
+                                      const double* __restrict__ u, long long count, double* __restrict__ out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const double u0 = u[2 * i], u1 = u[2 * i + 1];
+    double c;
+    if (copula == 2) {
+        const double eta = theta - 1.0;
+        const double num = theta * (1.0 + eta * (u0 + u1 - 2.0 * u0 * u1));
+        const double den = (1.0 + eta * (u0 + u1)) * (1.0 + eta * (1.0 - u0 - u1));
+        c = num / (den * den);
+    } else if (copula == 0) {
+        const double y0 = normcdfinv(u0), y1 = normcdfinv(u1);
+        const double om = 1.0 - rho * rho;
+        c = (isfinite(y0) && isfinite(y1)) ? exp(-(rho * rho * (y0 * y0 + y1 * y1) - 2.0 * rho * y0 * y1) / (2.0 * om)) / sqrt(om)
+                                           : NAN;
+    } else {
+        TDist D = tdist_make(nu);
+        const double y0 = t_quantile_iterative(D, u0), y1 = t_quantile_iterative(D, u1);
+        if (isfinite(y0) && isfinite(y1)) {
+            const double om = 1.0 - rho * rho;
+            const double qf = (y0 * y0 - 2.0 * rho * y0 * y1 + y1 * y1) / om;
+            c = kc * exp(-0.5 * (nu + 2.0) * log1p(qf / nu) + 0.5 * (nu + 1.0) * (log1p(y0 * y0 / nu) + log1p(y1 * y1 / nu)));
+        } else {
+            c = NAN;
+        }
+    }
+    out[i] = c;
+}
+
+}  // namespace cvar

@@ -1,0 +1,278 @@
+// cvar_math.cuh -- FP64 device primitives of the VaR solve (sm_100a).
+//
+// Two classes of functions live here:
+//   * the per-CELL primitives (exp2_fast, log2_fast, rcp_fast): branch-free, FP64-pipe only,
+//     no special-value handling -- callers guarantee finite in-range arguments;
+//   * the per-AXIS-POINT functions used once per (day, axis point): Phi via erf exactly as the
+//     reference forms it (utils/utils.py:17-22, quirk Q14), the normal quantile, and the
+//     Student-t quantile (iterative reference routine + Chebyshev table in the normal score).
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "cvar_coeffs.h"
+
+namespace cvar {
+
+// ---------------------------------------------------------------------------------------------
+// per-cell primitives
+// ---------------------------------------------------------------------------------------------
+
+// 2^t for finite t.  Results below 2^-1021 flush to ~1e-308 (never garbage), above 2^1023 saturate
+// to a huge finite number.  Max relative error ~2e-16 (degree-11 near-minimax on [-1/2, 1/2]).
+__device__ __forceinline__ double exp2_fast(double t) {
+    constexpr double c[] = CVAR_EXP2_POLY;
+    const double MAGIC = 6755399441055744.0;  // 1.5 * 2^52: adding it rounds t to the nearest integer
+    double kf = __dadd_rn(t, MAGIC);
+    int k = __double2loint(kf);
+    double r = __dadd_rn(t, -__dadd_rn(kf, -MAGIC));  // r in [-1/2, 1/2], exact
+    double p = c[11];
+#pragma unroll
+    for (int i = 10; i >= 0; --i) p = fma(p, r, c[i]);
+    k = max(-1021, min(k, 1023));
+    return __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
+}
+
+// 1/a for finite normal a: MUFU.RCP64H seed (2^-23) + two Newton steps on the FP64 pipe.
+__device__ __forceinline__ double rcp_fast(double a) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(a));
+    double e = fma(-a, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-a, r, 1.0);
+    r = fma(r, e, r);
+    return r;
+}
+
+// log2(t) for positive normal t.  log2(t) = e + (2/ln2) * atanh(s) with m in [sqrt(1/2), sqrt(2)),
+// s = (m-1)/(m+1).  Max relative error ~3e-16.
+__device__ __forceinline__ double log2_fast(double t) {
+    constexpr double c[] = CVAR_ATANH_POLY;
+    int hi = __double2hiint(t);
+    int e = (hi >> 20) - 1023;
+    int mhi = (hi & 0x000fffff) | 0x3ff00000;
+    if (mhi >= 0x3ff6a09e) {  // m >= ~sqrt(2): halve it (the polynomial range has 2 % slack)
+        mhi -= 0x00100000;
+        e += 1;
+    }
+    double m = __hiloint2double(mhi, __double2loint(t));
+    double f = m - 1.0;
+    double den = m + 1.0;
+    double rc = rcp_fast(den);
+    double s = f * rc;
+    s = fma(fma(-den, s, f), rc, s);  // one correction step: s is (f/den) to < 1 ulp
+    double z = s * s;
+    double p = c[6];
+#pragma unroll
+    for (int i = 5; i >= 0; --i) p = fma(p, z, c[i]);
+    double sc = s * CVAR_TWO_OVER_LN2;
+    return fma(sc, z * p, sc) + (double)e;
+}
+
+// ---------------------------------------------------------------------------------------------
+// per-axis-point functions
+// ---------------------------------------------------------------------------------------------
+
+// Phi(z) formed exactly like the reference: 0.5 * (1 + erf(z / sqrt(2)))  (absolute accuracy, Q14).
+__device__ __forceinline__ double phi_via_erf(double z) {
+    return 0.5 * (1.0 + erf(__ddiv_rn(z, 1.4142135623730951)));
+}
+
+// ----- Student-t distribution: iterative reference routine -------------------------------------
+
+// Continued fraction of the regularised incomplete beta function (modified Lentz).
+__device__ __noinline__ double ibeta_cf(double a, double b, double x) {
+    const double TINY = 1e-300;
+    double qab = a + b, qap = a + 1.0, qam = a - 1.0;
+    double c = 1.0;
+    double d = 1.0 - qab * x / qap;
+    if (fabs(d) < TINY) d = TINY;
+    d = 1.0 / d;
+    double h = d;
+    for (int m = 1; m <= 2000; ++m) {
+        double m2 = 2.0 * m;
+        double aa = m * (b - m) * x / ((qam + m2) * (a + m2));
+        d = 1.0 + aa * d;
+        if (fabs(d) < TINY) d = TINY;
+        c = 1.0 + aa / c;
+        if (fabs(c) < TINY) c = TINY;
+        d = 1.0 / d;
+        h *= d * c;
+        aa = -(a + m) * (qab + m) * x / ((a + m2) * (qap + m2));
+        d = 1.0 + aa * d;
+        if (fabs(d) < TINY) d = TINY;
+        c = 1.0 + aa / c;
+        if (fabs(c) < TINY) c = TINY;
+        d = 1.0 / d;
+        double del = d * c;
+        h *= del;
+        if (fabs(del - 1.0) < 2e-16) break;
+    }
+    return h;
+}
+
+// log of I_x(a, b) evaluated through the continued fraction at x (caller picks the convergent side).
+__device__ __noinline__ double log_ibeta_direct(double a, double b, double x, double lbeta) {
+    return a * log(x) + b * log1p(-x) - lbeta - log(a) + log(ibeta_cf(a, b, x));
+}
+
+struct TDist {
+    double nu;
+    double lbeta;    // log B(nu/2, 1/2)
+    double log_pdf0; // log of the density at 0
+};
+
+__device__ __forceinline__ TDist tdist_make(double nu) {
+    TDist d;
+    d.nu = nu;
+    d.lbeta = lgamma(0.5 * nu) + 0.5723649429247001 /* lgamma(1/2) */ - lgamma(0.5 * nu + 0.5);
+    d.log_pdf0 = -d.lbeta - 0.5 * log(nu);
+    return d;
+}
+
+// log F(-tau), tau > 0 (lower tail), relative accuracy everywhere.
+__device__ __noinline__ double t_log_lower_tail(const TDist& D, double tau) {
+    double nu = D.nu, a = 0.5 * nu, b = 0.5;
+    double t2 = tau * tau;
+    double x = nu / (nu + t2);  // I_x(a, b) = 2 F(-tau)
+    if (x < (a + 1.0) / (a + b + 2.0)) {
+        return log_ibeta_direct(a, b, x, D.lbeta) - 0.6931471805599453;
+    }
+    double xc = t2 / (nu + t2);  // 1 - x without cancellation
+    double ic = exp(log_ibeta_direct(b, a, xc, D.lbeta));
+    return log(0.5 - 0.5 * ic);
+}
+
+// F(tau) - 1/2 for tau >= 0, absolute accuracy near 0.
+__device__ __noinline__ double t_central_mass(const TDist& D, double tau) {
+    double nu = D.nu, a = 0.5 * nu, b = 0.5;
+    double t2 = tau * tau;
+    if (t2 == 0.0) return 0.0;
+    double xc = t2 / (nu + t2);
+    if (xc < (b + 1.0) / (a + b + 2.0)) return 0.5 * exp(log_ibeta_direct(b, a, xc, D.lbeta));
+    double x = nu / (nu + t2);
+    return 0.5 - 0.5 * exp(log_ibeta_direct(a, b, x, D.lbeta));
+}
+
+__device__ __forceinline__ double t_log_pdf(const TDist& D, double tau) {
+    return D.log_pdf0 - 0.5 * (D.nu + 1.0) * log1p(tau * tau / D.nu);
+}
+
+// |T_nu^{-1}(p)| for p in (0, 1/2]: Newton on log F in log|t| for the tail, Newton on F - 1/2 in the
+// centre.  Used to build the table and as the test reference; never on the per-solve path.
+__device__ __noinline__ double t_quantile_mag_iterative(const TDist& D, double p) {
+    if (!(p > 0.0)) return INFINITY;
+    if (p >= 0.5) return 0.0;
+    double nu = D.nu;
+    if (p < 0.2) {
+        // start right of the root: leading-order tail  F(-tau) <= c nu^{(nu-1)/2} tau^{-nu}
+        double lp = log(p);
+        double lc = D.log_pdf0 + 0.5 * (nu - 1.0) * log(nu);
+        double s = (lc - lp) / nu;  // log tau
+        double wn = -normcdfinv(p);
+        if (s < log(wn)) s = log(wn);
+        for (int it = 0; it < 200; ++it) {
+            double tau = exp(s);
+            double lF = t_log_lower_tail(D, tau);
+            double slope = -exp(t_log_pdf(D, tau) - lF) * tau;  // d log F / d log tau
+            double ds = (lp - lF) / slope;
+            if (ds > 2.0) ds = 2.0;
+            if (ds < -2.0) ds = -2.0;
+            s += ds;
+            if (fabs(ds) < 4e-16 * fmax(1.0, fabs(s))) break;
+        }
+        return exp(s);
+    }
+    double delta = 0.5 - p;  // exact for p in [1/4, 1/2]
+    double tau = -normcdfinv(p);
+    for (int it = 0; it < 200; ++it) {
+        double G = t_central_mass(D, tau) - delta;
+        double dt = -G / exp(t_log_pdf(D, tau));
+        double tn = tau + dt;
+        if (tn <= 0.0) tn = 0.5 * tau;
+        double change = fabs(tn - tau);
+        tau = tn;
+        if (change < 4e-16 * tau) break;
+    }
+    return tau;
+}
+
+// ----- Student-t quantile table ------------------------------------------------------------------
+// |T_nu^{-1}(Phi(w))| = |w| * rho(w) on w in [-W_MAX, 0]; rho is tabulated per interval as a Chebyshev
+// series of degree TQ_DEG (nu is a run constant, so the table is built once per plan).
+constexpr int TQ_INTERVALS = 256;
+constexpr int TQ_DEG = 9;
+constexpr double TQ_WMAX = 9.5;
+constexpr int TQ_TABLE_DOUBLES = TQ_INTERVALS * (TQ_DEG + 1);
+
+__device__ __forceinline__ double tq_ratio_exact(const TDist& D, double w /* < 0 */) {
+    double p = 0.5 * erfc(-w * 0.7071067811865476);
+    return t_quantile_mag_iterative(D, p) / (-w);
+}
+
+// one thread per (interval, node) computes a sample, then one thread per interval does the DCT
+__global__ void tq_table_build_kernel(double nu, double* __restrict__ table) {
+    __shared__ double f[TQ_DEG + 1];
+    const int N = TQ_DEG + 1;
+    int m = blockIdx.x;
+    int k = threadIdx.x;
+    const double h = TQ_WMAX / TQ_INTERVALS;
+    if (k < N) {
+        TDist D = tdist_make(nu);
+        double sk = cospi((k + 0.5) / N);
+        double w = -TQ_WMAX + h * (m + 0.5 * (1.0 + sk));
+        f[k] = tq_ratio_exact(D, w);
+    }
+    __syncthreads();
+    if (k < N) {
+        double acc = 0.0;
+        for (int i = 0; i < N; ++i) acc += f[i] * cospi(k * (i + 0.5) / N);
+        acc *= 2.0 / N;
+        if (k == 0) acc *= 0.5;
+        table[m * N + k] = acc;
+    }
+}
+
+// |T_nu^{-1}(p)| for p in (0, 1/2] from the table (leading-order tail beyond it).
+__device__ __forceinline__ double t_quantile_mag_table(const double* __restrict__ table, double nu, double tail_lc,
+                                                       double p) {
+    double w = normcdfinv(p);  // <= 0
+    if (w < -TQ_WMAX) return exp((tail_lc - log(p)) / nu);
+    const double inv_h = TQ_INTERVALS / TQ_WMAX;
+    double pos = (w + TQ_WMAX) * inv_h;
+    int m = min((int)pos, TQ_INTERVALS - 1);
+    double s = 2.0 * (pos - m) - 1.0;  // [-1, 1]
+    const double* c = table + m * (TQ_DEG + 1);
+    double b1 = 0.0, b2 = 0.0, s2 = 2.0 * s;
+#pragma unroll
+    for (int k = TQ_DEG; k >= 1; --k) {
+        double b0 = fma(s2, b1, c[k] - b2);
+        b2 = b1;
+        b1 = b0;
+    }
+    double ratio = fma(s, b1, c[0] - b2);
+    return -w * ratio;
+}
+
+// signed Student-t quantile of u in [0, 1]: -inf at 0, +inf at 1, NaN outside.
+__device__ __forceinline__ double t_quantile_table(const double* __restrict__ table, double nu, double tail_lc,
+                                                   double u) {
+    if (!(u >= 0.0 && u <= 1.0)) return NAN;
+    bool low = u < 0.5;
+    double p = low ? u : 1.0 - u;
+    if (p == 0.0) return low ? -INFINITY : INFINITY;
+    double mag = t_quantile_mag_table(table, nu, tail_lc, p);
+    return low ? -mag : mag;
+}
+
+__device__ __forceinline__ double t_quantile_iterative(const TDist& D, double u) {
+    if (!(u >= 0.0 && u <= 1.0)) return NAN;
+    bool low = u < 0.5;
+    double p = low ? u : 1.0 - u;
+    if (p == 0.0) return low ? -INFINITY : INFINITY;
+    double mag = t_quantile_mag_iterative(D, p);
+    return low ? -mag : mag;
+}
+
+}  // namespace cvar

@@ -1,0 +1,79 @@
+"""Patch the REFERENCE's own `ValueAtRiskCalcualtion` so that its hot path runs on the B200 backend.
+
+Use when the reference checkout is on sys.path (its `utils` package, its fitters, its data loader) and only
+the per-day solve should move to the GPU:
+
+    import cvar_b200.dropin as dropin
+    from utils.calc_var_class import ValueAtRiskCalcualtion      # the reference's class
+    dropin.install(ValueAtRiskCalcualtion)
+    ...
+    var = calculator.calc_var(obj_var=0.01)                      # now one CUDA launch
+
+`install` replaces `calc_var` and `compute_integral` (reference: utils/calc_var_class.py:95-212); nothing else
+of the reference is touched.  The GPU inputs are read from the same attributes the reference's methods read.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .backend import VarPlan
+from .inputs import HotPathInputs
+
+_FAMILY_BY_CLASS = {"GaussianCopulaVaR": "gaussian", "StudentCopulaVaR": "student", "PlackettCopulaVaR": "plackett"}
+
+
+def inputs_from_reference_object(v) -> HotPathInputs:
+    """HotPathInputs from a (reference) driver object's attributes."""
+    copula = getattr(v.VaRCalculationMethod, "copula_family", None) or _FAMILY_BY_CLASS[type(v.VaRCalculationMethod).__name__]
+    marginal = "single" if v.integrations_params_static is None else "mixture"
+    _, x, dx, _ = v.grids_generations_params
+    kw = dict(copula=copula, marginal=marginal, n=int(v.num_points), x=x, dx=dx, weights=np.asarray(v.weights, float),
+              ptf_mean=float(v.ptf_mean))
+    cp = v.copula_params
+    if copula == "gaussian":
+        kw["rho"] = float(np.atleast_1d(cp)[0])
+    elif copula == "student":
+        kw["nu"], kw["rho"] = float(cp[0]), float(cp[1])
+    else:
+        kw["theta"] = float(cp)
+    if marginal == "single":
+        kw["sigma"] = np.asarray(v.integrations_params_t[0], float)
+    else:
+        kw["probs"] = np.asarray(v.integrations_params_t[0], float)
+        kw["sigma_states"] = np.asarray(v.integrations_params_static, float)
+    if int(getattr(v, "dim", 2)) != 2:
+        raise NotImplementedError("the B200 backend covers two-asset portfolios")
+    return HotPathInputs(**kw)
+
+
+def _plan_for(v, first_guess, second_guess) -> VarPlan:
+    cache = v.__dict__.setdefault("_cvar_b200_plans", {})
+    key = (float(first_guess), float(second_guess[0]), float(second_guess[1]))
+    if key not in cache:
+        cache[key] = VarPlan(inputs_from_reference_object(v), first_guess=key[0], second_guess=key[1:])
+    return cache[key]
+
+
+def calc_var(self, obj_var=0.05, first_guess=-3, second_guess=(-3.5, -2)):
+    inp = inputs_from_reference_object(self)
+    res = _plan_for(self, first_guess, second_guess).solve(inp.day_params(), [obj_var], ptf_mean=self.ptf_mean)
+    return res.var[0]
+
+
+def compute_integral(self, bounds):
+    inp = inputs_from_reference_object(self)
+    return _plan_for(self, -3, (-3.5, -2)).strip_mass(inp.day_params(), np.asarray(bounds, float))
+
+
+def install(cls):
+    """Replace the hot-path methods of the reference's class; returns the originals for `uninstall`."""
+    originals = {"calc_var": cls.calc_var, "compute_integral": cls.compute_integral}
+    cls.calc_var = calc_var
+    cls.compute_integral = compute_integral
+    cls._cvar_b200_originals = originals
+    return originals
+
+
+def uninstall(cls):
+    for name, fn in getattr(cls, "_cvar_b200_originals", {}).items():
+        setattr(cls, name, fn)

@@ -23,6 +23,7 @@ import itertools
 import numpy as np
 
 from .inputs import HotPathInputs, make_inputs
+from .msm_layout import merge_states  # noqa: F401  (re-exported)
 
 # asset-level constants of SURVEY §8(d)
 GARCH_ASSETS = ((0.02, 0.09, 0.89, 1), (0.03, 0.08, 0.90, 2))       # omega, alpha, beta, seed
@@ -118,33 +119,6 @@ def hamilton_filter(returns: np.ndarray, vol_states: np.ndarray, P: np.ndarray) 
         pi = post / s
         out[t] = pi
     return out
-
-
-def merge_states(vol_states: np.ndarray, probs: np.ndarray, tol: float = 1e-6):
-    """Merge states of (numerically) equal volatility.
-
-    vol_states : (dim, S);  probs : (dim, T, S)
-    returns probs_by_state (T, dim, q) and sigma_states (dim, q), with the
-    vol levels rounded to multiples of ``tol`` exactly as the reference does
-    (msm_estimation.py:228-229) so that the merged sigma values are the same
-    doubles.
-    """
-    vol_states = np.asarray(vol_states, float)
-    probs = np.asarray(probs, float)
-    dim, T, _ = probs.shape
-    merged, levels = [], []
-    for d in range(dim):
-        rounded = np.round(vol_states[d] / tol) * tol
-        uniq, inv = np.unique(rounded, return_inverse=True)
-        # row-contiguous copies so every row is summed pairwise exactly like the reference's
-        # per-day `forecasts_array[i, n, :][inverse_idx == idx].sum()`
-        cols = [np.ascontiguousarray(probs[d][:, inv == j]).sum(axis=1) for j in range(len(uniq))]
-        merged.append(np.stack(cols, axis=1))
-        levels.append(uniq)
-    q = {len(u) for u in levels}
-    if len(q) != 1:
-        raise ValueError("assets merge to different numbers of vol levels")
-    return np.ascontiguousarray(np.stack(merged, axis=1)), np.array(levels)
 
 
 def msm_day_params(T: int, k: int = 8, assets=MSM_ASSETS):
