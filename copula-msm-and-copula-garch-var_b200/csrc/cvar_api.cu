@@ -99,7 +99,7 @@ __global__ void tq_table_check_kernel(double nu, const double* __restrict__ tabl
     TDist D = tdist_make(nu);
     const double exact = t_quantile_mag_iterative(D, p);
     const double fast = t_quantile_mag_table(table, nu, tail_lc, p);
-    const double err = fabs(fast - exact) / exact;
+    const double err = fabs(fast - exact) / fmax(exact, 0.1);  // relative in the tails, absolute (x10) around the median
     atomicMax(max_err_bits, (unsigned long long)__double_as_longlong(err));  // err >= 0: bit order == value order
 }
 
@@ -570,6 +570,49 @@ int cvar_copula_density_host(int32_t copula, double rho, double nu, double theta
     cudaFree(d_u);
     cudaFree(d_o);
     return (int)e;
+}
+
+// ---- FP64 pipe peak (roofline denominator) -----------------------------------------------------
+int cvar_fp64_peak_host(int device, double min_ms, double* tflops_out, double* ms_out) {
+    if (!tflops_out) return CVAR_ERR_NULL;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
+        cudaGetLastError();
+        return CVAR_ERR_NO_DEVICE;
+    }
+    if (device < 0 && cudaGetDevice(&device) != cudaSuccess) return CVAR_ERR_NO_DEVICE;
+    if (device >= ndev) return CVAR_ERR_NO_DEVICE;
+    DeviceGuard guard(device);
+    cudaDeviceProp prop;
+    CU_TRY(cudaGetDeviceProperties(&prop, device));
+    double* d_sink = nullptr;
+    CU_TRY(cudaMalloc(&d_sink, sizeof(double)));
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    const int blocks = prop.multiProcessorCount * 8, threads = 256;
+    int iters = 2000;
+    float ms = 0.f;
+    cudaError_t err = cudaSuccess;
+    for (int attempt = 0; attempt < 12; ++attempt) {
+        fp64_peak_kernel<<<blocks, threads>>>(iters, 1.0, d_sink);  // warm-up at this size
+        cudaEventRecord(e0);
+        fp64_peak_kernel<<<blocks, threads>>>(iters, 1.0, d_sink);
+        cudaEventRecord(e1);
+        err = cudaEventSynchronize(e1);
+        if (err != cudaSuccess) break;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (ms >= min_ms) break;
+        iters *= 2;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d_sink);
+    if (err != cudaSuccess) return (int)err;
+    const double flops = 2.0 * 64.0 * (double)iters * (double)blocks * (double)threads;  // 64 DFMA per thread per iteration
+    *tflops_out = flops / (ms * 1e-3) / 1e12;
+    if (ms_out) *ms_out = ms;
+    return CVAR_OK;
 }
 
 }  // extern "C"

@@ -75,8 +75,18 @@ __device__ __forceinline__ double log2_fast(double t) {
 // ---------------------------------------------------------------------------------------------
 
 // Phi(z) formed exactly like the reference: 0.5 * (1 + erf(z / sqrt(2)))  (absolute accuracy, Q14).
+// The left tail of u is quantised in steps of 2^-54 by the rounding of erf towards -1, and saturates to
+// exactly 0 / 1 beyond |z| ~ 8.3.  To land on the same quantum as a correctly rounded erf, |erf| >= ~0.84
+// is formed as 1 - erfc(|v|) (one rounding of an accurately known small number) instead of CUDA's 2-ulp erf.
+__device__ __forceinline__ double erf_like_reference(double v) {
+    const double a = fabs(v);
+    if (a < 1.0) return erf(v);
+    const double e = 1.0 - erfc(a);
+    return v < 0.0 ? -e : e;
+}
+
 __device__ __forceinline__ double phi_via_erf(double z) {
-    return 0.5 * (1.0 + erf(__ddiv_rn(z, 1.4142135623730951)));
+    return 0.5 * (1.0 + erf_like_reference(__ddiv_rn(z, 1.4142135623730951)));
 }
 
 // ----- Student-t distribution: iterative reference routine -------------------------------------

@@ -56,6 +56,7 @@ _PROTOTYPES = {
     "cvar_finalize_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "cvar_solve_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "cvar_test_special_host": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p]),
+    "cvar_fp64_peak_host": (C.c_int, [C.c_int, C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "cvar_copula_density_host": (C.c_int, [C.c_int32, C.c_double, C.c_double, C.c_double, C.c_void_p, C.c_int64, C.c_void_p, C.c_int]),
 }
 EXPORTED_SYMBOLS = tuple(_PROTOTYPES)

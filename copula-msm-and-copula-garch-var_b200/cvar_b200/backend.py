@@ -216,6 +216,13 @@ class VarPlan:
         return out
 
 
+def fp64_peak_tflops(device: int = -1, min_ms: float = 50.0) -> tuple[float, float]:
+    """(TFLOP/s, ms): FP64-pipe peak measured with a dependency-free DFMA micro-benchmark."""
+    t, ms = C.c_double(), C.c_double()
+    _lib.check(_lib.load().cvar_fp64_peak_host(int(device), float(min_ms), C.byref(t), C.byref(ms)), "cvar_fp64_peak_host")
+    return t.value, ms.value
+
+
 def solve_var(inputs: HotPathInputs, alphas, device: int | None = None, **plan_kw) -> SolveResult:
     """One-shot helper: build a plan for ``inputs`` and solve every (day, alpha)."""
     with VarPlan(inputs, device=device, **plan_kw) as plan:

@@ -120,8 +120,8 @@ typedef struct cvar_plan_info {
     int32_t ctas_per_sm;       /* resident solve CTAs per SM (occupancy query)         */
     int32_t threads_per_cta;
     int32_t smem_bytes_per_cta;
-    double tq_table_max_rel_err; /* Student only: measured max relative error of the device t-quantile
-                                    table against the iterative device routine; 0 otherwise */
+    double tq_table_max_rel_err; /* Student only: measured max of |table - iterative| / max(|iterative|, 0.1)
+                                    over 4 off-node probes per table interval; 0 otherwise */
     double last_kernel_ms;     /* device time of the last *_host solve (CUDA events), ms */
 } cvar_plan_info_t;
 
@@ -216,6 +216,13 @@ int cvar_test_special_host(cvar_plan_t* plan, int32_t which, const double* in, i
  */
 int cvar_copula_density_host(int32_t copula, double rho, double nu, double theta, const double* u, int64_t count,
                              double* out, int device);
+
+/*
+ * Measure the FP64-pipe peak of `device` with a dependency-free DFMA micro-benchmark running for at
+ * least `min_ms` milliseconds (the roofline denominator of this path: MEASURED_PEAKS.json only carries
+ * HBM and bf16 tensor peaks).  *tflops_out = 2 * DFMA issued / time.
+ */
+int cvar_fp64_peak_host(int device, double min_ms, double* tflops_out, double* ms_out);
 
 #ifdef __cplusplus
 }

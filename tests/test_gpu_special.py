@@ -38,9 +38,11 @@ def test_student_quantile_table_and_iterative(backend, nu):
         fast = plan.special(0, u)
         slow = plan.special(1, u)
         edge = plan.special(0, np.array([0.0, 1.0, 1.5, -0.1, np.nan]))
-    scale = np.maximum(np.abs(ref), 1e-3)
-    assert np.max(np.abs(slow - ref) / scale) < 2e-13
-    assert np.max(np.abs(fast - ref) / scale) < 2e-13
+    # relative accuracy in the tails, absolute accuracy (in units of 0.1) around the median, where the
+    # quantile crosses zero and only its absolute error enters the cell exponents
+    scale = np.maximum(np.abs(ref), 0.1)
+    assert np.max(np.abs(slow - ref) / scale) < 1e-13
+    assert np.max(np.abs(fast - ref) / scale) < 1e-13
     assert edge[0] == -np.inf and edge[1] == np.inf and np.all(np.isnan(edge[2:]))
 
 
@@ -66,6 +68,7 @@ def test_phi_via_erf_reproduces_reference_formula(backend):
         got = plan.special(4, z)
         q = plan.special(5, np.array([0.0, 1.0, 0.5, 1e-300, 5.551115123125783e-17]))
     assert np.max(np.abs(got - ref)) < 2.3e-16          # a 2-ulp erf at most moves Phi by one spacing of 2^-53
-    assert np.array_equal(got == 0, ref == 0) or np.sum((got == 0) != (ref == 0)) <= 2
+    # saturation to exactly 0 / 1 (|z| ~ 8.3) happens at the same grid points, give or take a rounding tie
+    assert np.sum((got == 0) != (ref == 0)) + np.sum((got == 1) != (ref == 1)) <= 2
     assert q[0] == -np.inf and q[1] == np.inf and q[2] == 0.0
     np.testing.assert_allclose(q[3:], stats.norm.ppf([1e-300, 5.551115123125783e-17]), rtol=1e-14)
