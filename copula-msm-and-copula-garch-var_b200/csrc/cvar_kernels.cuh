@@ -21,7 +21,7 @@ namespace cvar {
 
 constexpr int CTA_THREADS = 256;
 constexpr int CTA_WARPS = CTA_THREADS / 32;
-constexpr int ROWS_PER_GROUP = 4;  // adjacent outer rows sharing one pass over the inner axis (THICK mode)
+constexpr int CELLS_IN_FLIGHT = 4;  // independent cells per thread per loop trip (FP64 latency hiding)
 
 typedef unsigned short u16;
 
@@ -52,8 +52,7 @@ struct AlphaSet {
 // dynamic shared memory carve-up
 struct Smem {
     double* xs;     // [n] axis (membership searches)
-    double* in0;    // [n] inner-axis array 0
-    double* in1;    // [n] inner-axis array 1
+    double2* in;    // [n] inner-axis pair (.x, .y), interleaved so one 16-byte load feeds a cell
     double* out0;   // [n] outer-axis array 0
     double* out1;   // [n]
     double* out2;   // [n]
@@ -73,8 +72,7 @@ __device__ __forceinline__ Smem carve(unsigned char* base, int n) {
     Smem S;
     double* d = reinterpret_cast<double*>(base);
     S.xs = d;
-    S.in0 = d + npad;
-    S.in1 = d + 2 * npad;
+    S.in = reinterpret_cast<double2*>(d + npad);
     S.out0 = d + 3 * npad;
     S.out1 = d + 4 * npad;
     S.out2 = d + 5 * npad;
@@ -130,8 +128,7 @@ __device__ void stage0(const KernelParams& P, const double* __restrict__ dayp, c
             }
         }
         if (COPULA == 2) {
-            S.in0[i] = u[1];
-            S.in1[i] = a[1];
+            S.in[i] = make_double2(u[1], a[1]);
             S.out0[i] = u[0];
             S.out1[i] = a[0];
         } else {
@@ -150,16 +147,14 @@ __device__ void stage0(const KernelParams& P, const double* __restrict__ dayp, c
             }
             const double l1 = fmax(log2(a[1]), -1100.0);
             if (COPULA == 0) {
-                S.in0[i] = P.g_in_scale * y[1];
-                S.in1[i] = l1;
+                S.in[i] = make_double2(P.g_in_scale * y[1], l1);
                 S.out0[i] = P.g_out_scale * y[0];
                 S.out1[i] = a[0] * P.g_const * exp(0.5 * y[0] * y[0]);
             } else {
                 const double hp = 0.5 * (P.nu + 1.0);
                 const double c1 = 1.0 + y[1] * y[1] / P.nu;
                 const double c0 = 1.0 + y[0] * y[0] / P.nu;
-                S.in0[i] = P.g_in_scale * y[1];
-                S.in1[i] = fmax(l1 + hp * log2(c1), -1100.0);
+                S.in[i] = make_double2(P.g_in_scale * y[1], fmax(l1 + hp * log2(c1), -1100.0));
                 S.out0[i] = P.g_out_scale * y[0];
                 S.out1[i] = c0;
                 S.out2[i] = a[0] * P.g_const * exp2(hp * log2(c0));
@@ -188,18 +183,19 @@ __device__ __forceinline__ int count_le(const double* __restrict__ xs, double g,
     return lo;
 }
 
-// ctarget[i] = max(#{x <= g_i(q)}, cmin) for every outer row; the search is confined to [slo[i], shi[i]]
+// c = max(#{x <= g_i(q)}, cmin) for outer row i; the search is confined to [lo, hi]
+__device__ __forceinline__ int count_row(const KernelParams& P, const Smem& S, double q, int i, int lo, int hi) {
+    const double g = inner_bound(q, S.xs[i], P.w0, P.w1);
+    if (lo > 0 && !(S.xs[lo - 1] <= g)) lo = 0;  // stored bounds are clipped at cmin; stay exact
+    return max(count_le(S.xs, g, lo, hi), P.cmin);
+}
+
+// ctarget[i] = count_row(q) for every outer row (thread t owns rows t, t + CTA_THREADS, ...)
 __device__ __forceinline__ void count_rows(const KernelParams& P, const Smem& S, double q, u16* ctarget,
                                            const u16* slo, const u16* shi) {
     const int n = P.n;
-    for (int i = threadIdx.x; i < n; i += CTA_THREADS) {
-        const double g = inner_bound(q, S.xs[i], P.w0, P.w1);
-        int lo = slo ? (int)slo[i] : 0;
-        int hi = shi ? (int)shi[i] : n;
-        if (lo > 0 && !(S.xs[lo - 1] <= g)) lo = 0;  // stored bounds are clipped at cmin; stay exact
-        int c = count_le(S.xs, g, lo, hi);
-        ctarget[i] = (u16)max(c, P.cmin);
-    }
+    for (int i = threadIdx.x; i < n; i += CTA_THREADS)
+        ctarget[i] = (u16)count_row(P, S, q, i, slo ? (int)slo[i] : 0, shi ? (int)shi[i] : n);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -291,98 +287,63 @@ __device__ __forceinline__ StripResult block_reduce(const Smem& S, int& parity, 
     return r;
 }
 
-// Sum of the cell weights with inner index in [ca[i], cb[i]) for every outer row i (ca == nullptr: cmin).
-// THICK: a warp walks ROWS_PER_GROUP adjacent rows with its lanes across the inner axis.
-// THIN : one thread per row (strips a few cells wide).
+// One strip of the bisection.
+//
+// Thread t owns outer rows t, t + CTA_THREADS, ... for the whole solve: it finds the row's new boundary
+// index by an exact binary search (when q_new is given), then walks the row's cells [a, b) itself with
+// CELLS_IN_FLIGHT independent cells per trip.  Adjacent lanes own adjacent rows, whose ranges are shifted
+// by about one column, so the 16-byte shared-memory loads of a warp fall on consecutive addresses.
+// There is no per-strip barrier besides the one inside the block reduction, and the boundary arrays are
+// only ever touched by their owning thread.
+//   bound arrays: ca == nullptr means the constant lower end cmin; cnew (may alias ca or cb) receives
+//   count(q_new) searched inside [slo[i], shi[i]] before the row is summed.
 template <int COPULA>
-__device__ StripResult strip_sum(const KernelParams& P, const Smem& S, const Live& L, int& parity, const u16* ca,
-                                 const u16* cb, bool thick, bool poison_mode) {
+__device__ StripResult strip_pass(const KernelParams& P, const Smem& S, const Live& L, int& parity, bool do_count,
+                                  double q_new, u16* cnew, const u16* slo, const u16* shi, const u16* ca,
+                                  const u16* cb, bool poison_mode) {
     const int n = P.n;
     double total = 0.0;
     unsigned cells = 0;
     bool poison = false;
-    if (thick) {
-        __syncthreads();  // bounds were written one thread per row
-        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-        const int ngroups = (n + ROWS_PER_GROUP - 1) / ROWS_PER_GROUP;
-        for (int grp = warp; grp < ngroups; grp += CTA_WARPS) {
-            const int i0 = grp * ROWS_PER_GROUP;
-            int js[ROWS_PER_GROUP], je[ROWS_PER_GROUP];
-            int jmin = 0x7fffffff, jmax = 0;
-#pragma unroll
-            for (int r = 0; r < ROWS_PER_GROUP; ++r) {
-                const int i = i0 + r;
-                int s = 0, e = 0;
-                if (i < n) {
-                    s = ca ? (int)ca[i] : P.cmin;
-                    e = (int)cb[i];
-                    if (e > s) {
-                        if (lane == 0) cells += (unsigned)(e - s);
-                        if (i < L.i_lo || i >= L.i_hi) {
-                            poison = true;
-                            e = s;
-                        } else {
-                            if (s < L.j_lo || e > L.j_hi) poison = true;
-                            s = max(s, L.j_lo);
-                            e = min(e, L.j_hi);
-                        }
-                    }
-                    if (e <= s) s = e = 0;
-                }
-                js[r] = s;
-                je[r] = e;
-                if (e > s) {
-                    jmin = min(jmin, s);
-                    jmax = max(jmax, e);
-                }
-            }
-            if (jmin >= jmax) continue;
-            Row<COPULA> row[ROWS_PER_GROUP];
-            double acc[ROWS_PER_GROUP];
-#pragma unroll
-            for (int r = 0; r < ROWS_PER_GROUP; ++r) {
-                row[r].load(P, S, min(i0 + r, n - 1));
-                acc[r] = 0.0;
-            }
-            for (int j = jmin + lane; j < jmax; j += 32) {
-                const double a = S.in0[j], b = S.in1[j];
-#pragma unroll
-                for (int r = 0; r < ROWS_PER_GROUP; ++r) {
-                    const double w = row[r].cell(P, a, b);
-                    if (j >= js[r] && j < je[r]) acc[r] += w;
-                }
-            }
-#pragma unroll
-            for (int r = 0; r < ROWS_PER_GROUP; ++r) total = fma(row[r].fac, acc[r], total);
+    for (int i = threadIdx.x; i < n; i += CTA_THREADS) {
+        if (do_count) cnew[i] = (u16)count_row(P, S, q_new, i, slo ? (int)slo[i] : 0, shi ? (int)shi[i] : n);
+        int s = ca ? (int)ca[i] : P.cmin;
+        int e = (int)cb[i];
+        if (e <= s) continue;
+        cells += (unsigned)(e - s);
+        if (i < L.i_lo || i >= L.i_hi) {
+            poison = true;
+            continue;
         }
-    } else {
-        for (int i = threadIdx.x; i < n; i += CTA_THREADS) {
-            int s = ca ? (int)ca[i] : P.cmin;
-            int e = (int)cb[i];
-            if (e <= s) continue;
-            cells += (unsigned)(e - s);
-            if (i < L.i_lo || i >= L.i_hi) {
-                poison = true;
-                continue;
-            }
-            if (s < L.j_lo || e > L.j_hi) poison = true;
-            s = max(s, L.j_lo);
-            e = min(e, L.j_hi);
-            if (e <= s) continue;
-            Row<COPULA> row;
-            row.load(P, S, i);
-            double acc = 0.0;
-            for (int j = s; j < e; ++j) acc += row.cell(P, S.in0[j], S.in1[j]);
-            total = fma(row.fac, acc, total);
+        if (s < L.j_lo || e > L.j_hi) poison = true;
+        s = max(s, L.j_lo);
+        e = min(e, L.j_hi);
+        if (e <= s) continue;
+        Row<COPULA> row;
+        row.load(P, S, i);
+        double acc[CELLS_IN_FLIGHT];
+#pragma unroll
+        for (int c = 0; c < CELLS_IN_FLIGHT; ++c) acc[c] = 0.0;
+        int j = s;
+        for (; j + CELLS_IN_FLIGHT <= e; j += CELLS_IN_FLIGHT) {
+            double2 v[CELLS_IN_FLIGHT];
+#pragma unroll
+            for (int c = 0; c < CELLS_IN_FLIGHT; ++c) v[c] = S.in[j + c];
+#pragma unroll
+            for (int c = 0; c < CELLS_IN_FLIGHT; ++c) acc[c] += row.cell(P, v[c].x, v[c].y);
         }
+        for (; j < e; ++j) {
+            const double2 v = S.in[j];
+            acc[0] += row.cell(P, v.x, v.y);
+        }
+        double rowsum = acc[0];
+#pragma unroll
+        for (int c = 1; c < CELLS_IN_FLIGHT; ++c) rowsum += acc[c];
+        total = fma(row.fac, rowsum, total);
     }
     StripResult r = block_reduce(S, parity, total, cells, poison && poison_mode);
     if (r.poisoned) r.mass = NAN;
     return r;
-}
-
-__device__ __forceinline__ bool is_thick(const KernelParams& P, double a, double b) {
-    return fabs((b - a) / P.w0) >= P.thick_width;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -416,27 +377,22 @@ solve_kernel(KernelParams P, const double* __restrict__ day_params, long long T,
         const double alpha = A.a[ia];
         unsigned long long ncell = 0;
         // --- probe 1: F(first)  (calc_var_class.py:114-119)
-        count_rows(P, S, P.first, S.c[0], nullptr, nullptr);
         if (!have_f3) {
-            f3 = strip_sum<COPULA>(P, S, L, parity, nullptr, S.c[0], true, poison_mode);
+            f3 = strip_pass<COPULA>(P, S, L, parity, true, P.first, S.c[0], nullptr, nullptr, nullptr, S.c[0], poison_mode);
             have_f3 = true;
         } else {
-            __syncthreads();
+            count_rows(P, S, P.first, S.c[0], nullptr, nullptr);
         }
         ncell += f3.cells;
         // --- probe 2  (:125-142)
         double lo2, hi2;
         if (f3.mass >= alpha) { lo2 = P.second_lo; hi2 = P.first; } else { lo2 = P.first; hi2 = P.second_hi; }
         double prev_upper = (lo2 == P.second_lo) ? P.second_lo : P.first;  // Q6
-        const u16 *pa, *pb;
-        if (lo2 == P.first) {
-            count_rows(P, S, hi2, S.c[1], S.c[0], nullptr);
-            pa = S.c[0]; pb = S.c[1];
-        } else {
-            count_rows(P, S, lo2, S.c[1], nullptr, S.c[0]);
-            pa = S.c[1]; pb = S.c[0];
-        }
-        const StripResult s2 = strip_sum<COPULA>(P, S, L, parity, pa, pb, is_thick(P, lo2, hi2), poison_mode);
+        StripResult s2;
+        if (lo2 == P.first)   // strip (first, second_hi]: new upper boundary, searched above c[0]
+            s2 = strip_pass<COPULA>(P, S, L, parity, true, hi2, S.c[1], S.c[0], nullptr, S.c[0], S.c[1], poison_mode);
+        else                  // strip (second_lo, first]: new lower boundary, searched below c[0]
+            s2 = strip_pass<COPULA>(P, S, L, parity, true, lo2, S.c[1], nullptr, S.c[0], S.c[1], S.c[0], poison_mode);
         ncell += s2.cells;
         double R = (lo2 == P.first) ? f3.mass + s2.mass : f3.mass - s2.mass;
         if ((P.compat & 2u) == 0 && lo2 == P.first) prev_upper = hi2;  // intended behaviour: R = F(hi2)
@@ -462,10 +418,9 @@ solve_kernel(KernelParams P, const double* __restrict__ day_params, long long T,
         if (kase != 4) {
             for (int k = 0; k < P.max_iter; ++k) {
                 const double mid = (lo + hi) / 2;
-                const double a = stack ? lo : mid, b = stack ? mid : hi;
-                count_rows(P, S, mid, cm, cl, ch);
-                const StripResult s = strip_sum<COPULA>(P, S, L, parity, stack ? cl : cm, stack ? cm : ch,
-                                                        is_thick(P, a, b), poison_mode);
+                const double a = stack ? lo : mid;
+                const StripResult s = strip_pass<COPULA>(P, S, L, parity, true, mid, cm, cl, ch, stack ? cl : cm,
+                                                         stack ? cm : ch, poison_mode);
                 ncell += s.cells;
                 R = (a == prev_upper) ? R + s.mass : R - s.mass;  // adjust_integral (:241-246)
                 if (R == 0.0) zer |= 1u << k;
@@ -508,9 +463,8 @@ strip_mass_kernel(KernelParams P, const double* __restrict__ day_params, const d
     int parity = 0;
     const double lo = bounds[2 * day], hi = bounds[2 * day + 1];
     count_rows(P, S, lo, S.c[0], nullptr, nullptr);
-    count_rows(P, S, hi, S.c[1], nullptr, nullptr);
     // an inverted pair yields an empty strip (cb <= ca), like the reference's empty np.where
-    const StripResult s = strip_sum<COPULA>(P, S, L, parity, S.c[0], S.c[1], true, poison_mode);
+    const StripResult s = strip_pass<COPULA>(P, S, L, parity, true, hi, S.c[1], nullptr, nullptr, S.c[0], S.c[1], poison_mode);
     if (threadIdx.x == 0) {
         out[day] = s.mass;
         if (cells_out) cells_out[day] = s.cells;

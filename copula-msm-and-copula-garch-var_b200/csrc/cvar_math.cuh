@@ -19,18 +19,22 @@ namespace cvar {
 // per-cell primitives
 // ---------------------------------------------------------------------------------------------
 
-// 2^t for finite t.  Results below 2^-1021 flush to ~1e-308 (never garbage), above 2^1023 saturate
-// to a huge finite number.  Max relative error ~2e-16 (degree-11 near-minimax on [-1/2, 1/2]).
+// Polynomial coefficients live in constant memory so that every Horner step is ONE instruction
+// (DFMA with a constant-bank operand); as literals they cost two UMOV per coefficient per use.
+__constant__ double kExp2Coef[CVAR_EXP2_POLY_DEG + 1] = CVAR_EXP2_POLY;
+__constant__ double kAtanhCoef[CVAR_ATANH_POLY_DEG + 1] = CVAR_ATANH_POLY;
+
+// 2^t for finite t <= ~1000.  Results below 2^-1021 flush to ~1e-308 (never garbage).  Max relative
+// error ~2e-16 (degree-11 near-minimax on [-1/2, 1/2]).
 __device__ __forceinline__ double exp2_fast(double t) {
-    constexpr double c[] = CVAR_EXP2_POLY;
     const double MAGIC = 6755399441055744.0;  // 1.5 * 2^52: adding it rounds t to the nearest integer
-    double kf = __dadd_rn(t, MAGIC);
+    const double kf = __dadd_rn(t, MAGIC);
     int k = __double2loint(kf);
-    double r = __dadd_rn(t, -__dadd_rn(kf, -MAGIC));  // r in [-1/2, 1/2], exact
-    double p = c[11];
+    const double r = __dadd_rn(t, -__dadd_rn(kf, -MAGIC));  // r in [-1/2, 1/2], exact
+    double p = kExp2Coef[11];
 #pragma unroll
-    for (int i = 10; i >= 0; --i) p = fma(p, r, c[i]);
-    k = max(-1021, min(k, 1023));
+    for (int i = 10; i >= 0; --i) p = fma(p, r, kExp2Coef[i]);
+    k = max(k, -1021);
     return __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
 }
 
@@ -45,28 +49,25 @@ __device__ __forceinline__ double rcp_fast(double a) {
     return r;
 }
 
-// log2(t) for positive normal t.  log2(t) = e + (2/ln2) * atanh(s) with m in [sqrt(1/2), sqrt(2)),
-// s = (m-1)/(m+1).  Max relative error ~3e-16.
+// log2(t) for positive normal t.  log2(t) = e + (2/ln2) * atanh(s) with m = t * 2^-e in
+// [sqrt(1/2), sqrt(2)), s = (m-1)/(m+1).  Max relative error ~4e-16.
 __device__ __forceinline__ double log2_fast(double t) {
-    constexpr double c[] = CVAR_ATANH_POLY;
-    int hi = __double2hiint(t);
-    int e = (hi >> 20) - 1023;
-    int mhi = (hi & 0x000fffff) | 0x3ff00000;
-    if (mhi >= 0x3ff6a09e) {  // m >= ~sqrt(2): halve it (the polynomial range has 2 % slack)
-        mhi -= 0x00100000;
-        e += 1;
-    }
-    double m = __hiloint2double(mhi, __double2loint(t));
-    double f = m - 1.0;
-    double den = m + 1.0;
-    double rc = rcp_fast(den);
+    const int hi = __double2hiint(t);
+    // e = floor(log2 t), +1 when the mantissa is above ~sqrt(2) (the polynomial range has 2 % slack)
+    const int e = ((hi + (0x00100000 - 0x0006a09e)) >> 20) - 1023;
+    const double scale = __hiloint2double((1023 - e) << 20, 0);  // 2^-e
+    const double f = fma(t, scale, -1.0);                         // m - 1, exact
+    const double den = fma(t, scale, 1.0);                        // m + 1
+    double rc;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(rc) : "d"(den));
+    rc = fma(rc, fma(-den, rc, 1.0), rc);                         // 2^-46
     double s = f * rc;
-    s = fma(fma(-den, s, f), rc, s);  // one correction step: s is (f/den) to < 1 ulp
-    double z = s * s;
-    double p = c[6];
+    s = fma(fma(-den, s, f), rc, s);                              // s = f/den to ~1 ulp
+    const double z = s * s;
+    double p = kAtanhCoef[6];
 #pragma unroll
-    for (int i = 5; i >= 0; --i) p = fma(p, z, c[i]);
-    double sc = s * CVAR_TWO_OVER_LN2;
+    for (int i = 5; i >= 0; --i) p = fma(p, z, kAtanhCoef[i]);
+    const double sc = s * CVAR_TWO_OVER_LN2;
     return fma(sc, z * p, sc) + (double)e;
 }
 

@@ -18,14 +18,14 @@ regions = {
     "0.45..0.5": rng.uniform(0.45, 0.5, 3000),
     "0.5..1": rng.uniform(0.5, 1, 3000),
 }
-for nu in (2.01, 5.3, 30.0, 50.0):
+for nu in (2.01, 2.5, 4.0, 5.3, 30.0, 50.0):
     inp = make_inputs("student", "single", 64, nu=nu, sigma=np.ones((1, 2)))
     with VarPlan(inp) as plan:
         print(f"nu={nu}: table-vs-iterative max rel err {plan.info().tq_table_max_rel_err:.3e}")
         for name, u in regions.items():
             ref = stats.t.ppf(u, df=nu)
             fast, slow = plan.special(0, u), plan.special(1, u)
-            sc = np.maximum(np.abs(ref), 1e-3)
+            sc = np.maximum(np.abs(ref), 0.1)
             ef, es = np.abs(fast - ref) / sc, np.abs(slow - ref) / sc
             print(f"   {name:14s} fast {ef.max():.2e} (u={u[ef.argmax()]:.3e})  slow {es.max():.2e} (u={u[es.argmax()]:.3e})"
                   f"  fast-vs-slow {np.max(np.abs(fast-slow)/sc):.2e}")
