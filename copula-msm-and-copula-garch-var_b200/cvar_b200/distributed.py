@@ -35,8 +35,10 @@ def gather_trajectories(traj_local: torch.Tensor, T_total: int, group=None) -> t
         pad = torch.zeros((na, per - t_local, two), dtype=traj_local.dtype, device=traj_local.device)
         traj_local = torch.cat([traj_local, pad], dim=1)
     traj_local = traj_local.contiguous()
-    gathered = torch.empty((world, na, per, two), dtype=traj_local.dtype, device=traj_local.device)
-    dist.all_gather_into_tensor(gathered, traj_local, group=group)
+    # flat buffers: the one layout both NCCL and gloo accept for all_gather_into_tensor
+    flat = torch.empty(world * na * per * two, dtype=traj_local.dtype, device=traj_local.device)
+    dist.all_gather_into_tensor(flat, traj_local.view(-1), group=group)
+    gathered = flat.view(world, na, per, two)
     # (world, na, per, 2) -> (na, world * per, 2), then drop the padding of the ragged tail
     out = gathered.permute(1, 0, 2, 3).reshape(na, world * per, two)
     return out[:, :T_total, :].contiguous()

@@ -18,6 +18,22 @@ def backend(cuda_device):
     return be
 
 
+def _mp_t_quantile(u, nu):
+    """Student-t quantile to 30 digits (mpmath): root of the regularised incomplete beta form of the cdf."""
+    import mpmath as mp
+    mp.mp.dps = 30
+    um = mp.mpf(u)
+    low = um < mp.mpf("0.5")
+    p = um if low else 1 - um
+    if p == mp.mpf("0.5"):
+        return 0.0
+    nu_m = mp.mpf(nu)
+    cdf_lower = lambda t: mp.betainc(nu_m / 2, mp.mpf("0.5"), 0, nu_m / (nu_m + t * t), regularized=True) / 2
+    guess = abs(float(stats.t.ppf(float(p), df=nu)))
+    tau = mp.findroot(lambda t: mp.log(cdf_lower(t)) - mp.log(p), guess)
+    return float(-tau if low else tau)
+
+
 def _u_grid():
     rng = np.random.default_rng(0)
     u = np.concatenate([
@@ -41,8 +57,18 @@ def test_student_quantile_table_and_iterative(backend, nu):
     # relative accuracy in the tails, absolute accuracy (in units of 0.1) around the median, where the
     # quantile crosses zero and only its absolute error enters the cell exponents
     scale = np.maximum(np.abs(ref), 0.1)
-    assert np.max(np.abs(slow - ref) / scale) < 1e-13
-    assert np.max(np.abs(fast - ref) / scale) < 1e-13
+    err_fast, err_slow = np.abs(fast - ref) / scale, np.abs(slow - ref) / scale
+    # the two device routines are independent of each other (table in the normal score vs Newton on the cdf)
+    assert np.max(np.abs(fast - slow) / scale) < 5e-14
+    # SciPy itself is only good to ~1e-11 at a few spots (closed forms for nu = 4 around the median, nu = 2.5
+    # near u = 0.21): agree with it to 1e-10 everywhere, to 1e-13 on 99 % of the grid, and let mpmath
+    # arbitrate on the points of largest disagreement.
+    assert max(err_fast.max(), err_slow.max()) < 1e-10
+    assert np.quantile(err_fast, 0.99) < 1e-13 and np.quantile(err_slow, 0.99) < 1e-13
+    worst = np.argsort(err_fast)[-12:]
+    exact = np.array([_mp_t_quantile(float(u[i]), nu) for i in worst])
+    assert np.max(np.abs(fast[worst] - exact) / np.maximum(np.abs(exact), 0.1)) < 1e-13
+    assert np.max(np.abs(slow[worst] - exact) / np.maximum(np.abs(exact), 0.1)) < 1e-13
     assert edge[0] == -np.inf and edge[1] == np.inf and np.all(np.isnan(edge[2:]))
 
 
