@@ -4,6 +4,7 @@
 // Student-t quantile table, the axis on the device), launches, and the H2D/D2H copies of the
 // `*_host` entry points.  There is no CPU implementation of the solve in this library.
 #include <cuda_runtime.h>
+#include <cub/device/device_radix_sort.cuh>
 
 #include <algorithm>
 #include <cmath>
@@ -38,6 +39,10 @@ struct cvar_plan {
     void* d_ws;
     size_t ws_bytes;
     int* d_k;  // [CVAR_MAX_ALPHA] iteration counts
+    // launch-order scratch (keys, indices, sorted copies, cub temp), grown on demand
+    void* d_sched;
+    size_t sched_bytes;
+    double rho_eff;
 };
 
 #define CU_TRY(expr)                          \
@@ -103,19 +108,53 @@ __global__ void tq_table_check_kernel(double nu, const double* __restrict__ tabl
     atomicMax(max_err_bits, (unsigned long long)__double_as_longlong(err));  // err >= 0: bit order == value order
 }
 
+// Days in ascending order of the portfolio-variance proxy (most expensive solves first); nullptr when the
+// batch fits the resident CTA slots anyway.
+int make_order(cvar_plan* p, const double* d_day, int64_t T, cudaStream_t st, const int** order_out) {
+    *order_out = nullptr;
+    if (T <= 2LL * p->sm_count * std::max(p->ctas_per_sm, 1)) return 0;
+    const size_t b_key = align256(sizeof(float) * T), b_idx = align256(sizeof(int) * T);
+    size_t b_tmp = 0;
+    CU_TRY(cub::DeviceRadixSort::SortPairs(nullptr, b_tmp, (const float*)nullptr, (float*)nullptr, (const int*)nullptr,
+                                           (int*)nullptr, (int)T, 0, 32, st));
+    b_tmp = align256(b_tmp);
+    const size_t need = 2 * b_key + 2 * b_idx + b_tmp;
+    if (need > p->sched_bytes) {
+        if (p->d_sched) CU_TRY(cudaFree(p->d_sched));
+        p->d_sched = nullptr;
+        p->sched_bytes = 0;
+        CU_TRY(cudaMalloc(&p->d_sched, need));
+        p->sched_bytes = need;
+    }
+    char* base = (char*)p->d_sched;
+    float* key_in = (float*)base;
+    float* key_out = (float*)(base + b_key);
+    int* idx_in = (int*)(base + 2 * b_key);
+    int* idx_out = (int*)(base + 2 * b_key + b_idx);
+    void* tmp = base + 2 * b_key + 2 * b_idx;
+    order_key_kernel<<<(unsigned)((T + 255) / 256), 256, 0, st>>>(p->kp, d_day, (long long)T, p->rho_eff, key_in, idx_in);
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cub::DeviceRadixSort::SortPairs(tmp, b_tmp, key_in, key_out, idx_in, idx_out, (int)T, 0, 32, st));
+    *order_out = idx_out;
+    return 0;
+}
+
 int launch_solve(cvar_plan* p, const double* d_day, int64_t T, const AlphaSet& A, uint32_t* d_traj, double* d_mass,
                  unsigned long long* d_cells, cudaStream_t st) {
     if (T == 0) return 0;
+    const int* order = nullptr;
+    int rc = make_order(p, d_day, T, st, &order);
+    if (rc) return rc;
     dim3 grid((unsigned)T), block(CTA_THREADS);
     switch (p->desc.copula) {
         case CVAR_COPULA_GAUSSIAN:
-            solve_kernel<0><<<grid, block, p->smem_bytes, st>>>(p->kp, d_day, (long long)T, A, d_traj, d_mass, d_cells);
+            solve_kernel<0><<<grid, block, p->smem_bytes, st>>>(p->kp, d_day, (long long)T, A, order, d_traj, d_mass, d_cells);
             break;
         case CVAR_COPULA_STUDENT:
-            solve_kernel<1><<<grid, block, p->smem_bytes, st>>>(p->kp, d_day, (long long)T, A, d_traj, d_mass, d_cells);
+            solve_kernel<1><<<grid, block, p->smem_bytes, st>>>(p->kp, d_day, (long long)T, A, order, d_traj, d_mass, d_cells);
             break;
         default:
-            solve_kernel<2><<<grid, block, p->smem_bytes, st>>>(p->kp, d_day, (long long)T, A, d_traj, d_mass, d_cells);
+            solve_kernel<2><<<grid, block, p->smem_bytes, st>>>(p->kp, d_day, (long long)T, A, order, d_traj, d_mass, d_cells);
     }
     return (int)cudaGetLastError();
 }
@@ -272,7 +311,6 @@ int cvar_plan_create(const cvar_desc_t* desc, const double* x, const double* dx,
     kp.cmin = (int)(std::upper_bound(x, x + n, desc->clip_lo) - x);
     double dx_min = INFINITY;
     for (int i = 1; i < n; ++i) dx_min = std::min(dx_min, x[i] - x[i - 1]);
-    kp.thick_width = 24.0 * dx_min;
     const double LOG2E = 1.4426950408889634;
     if (desc->copula == CVAR_COPULA_GAUSSIAN) {
         const double om = 1.0 - desc->rho * desc->rho;
@@ -289,6 +327,12 @@ int cvar_plan_create(const cvar_desc_t* desc, const double* x, const double* dx,
                      std::sqrt(om);
         const double lbeta = std::lgamma(0.5 * nu) + std::lgamma(0.5) - std::lgamma(0.5 * nu + 0.5);
         kp.tq_tail_lc = (-lbeta - 0.5 * std::log(nu)) + 0.5 * (nu - 1.0) * std::log(nu);
+    }
+    // correlation used by the launch-order proxy only (Plackett: Spearman's rho of the family)
+    p->rho_eff = desc->rho;
+    if (desc->copula == CVAR_COPULA_PLACKETT) {
+        const double th = desc->theta;
+        p->rho_eff = std::fabs(th - 1.0) < 1e-9 ? 0.0 : ((th + 1.0) / (th - 1.0) - 2.0 * th * std::log(th) / ((th - 1.0) * (th - 1.0)));
     }
     // iterations: every bracket's own requirement, and the largest of them is what the kernel records
     FinalizeParams& fp = p->fp;
@@ -375,6 +419,7 @@ int cvar_plan_destroy(cvar_plan_t* p) {
     cudaFree(p->d_tq_table);
     cudaFree(p->d_ws);
     cudaFree(p->d_k);
+    cudaFree(p->d_sched);
     if (p->ev0) cudaEventDestroy(p->ev0);
     if (p->ev1) cudaEventDestroy(p->ev1);
     if (p->stream) cudaStreamDestroy(p->stream);

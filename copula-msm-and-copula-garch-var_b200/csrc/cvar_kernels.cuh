@@ -32,7 +32,6 @@ struct KernelParams {
     int cmin;  // #{x <= clip_lo}: first inner index that can ever belong to a strip
     double rho, nu, theta, w0, w1;
     double neg_inf, first, second_lo, second_hi, min_var, max_var;
-    double thick_width;  // strips at least this wide (in units of the inner coordinate) use warp-per-row-group
     // copula constants prepared on the host
     double g_in_scale;   // gaussian: sqrt(kappa*log2e)          student: 1/sqrt(nu(1-rho^2))
     double g_out_scale;  // gaussian: sgn(rho) sqrt(log2e/(2(1-rho^2)))   student: rho/sqrt(nu(1-rho^2))
@@ -183,6 +182,18 @@ __device__ __forceinline__ int count_le(const double* __restrict__ xs, double g,
     return lo;
 }
 
+// Row ownership.  Rows are dealt to warps in blocks of 32 (lane = row within the block, so adjacent lanes walk
+// adjacent rows); the block-to-warp order alternates direction every round (0..7, 7..0, 0..7, ...) because
+// the strip length falls off monotonically with the row index and a fixed order would always hand warp 0
+// the longest rows.  The mapping is fixed for the whole solve: a thread only ever touches its own rows'
+// boundary entries, which is why no barrier separates the boundary search from the cell walk.
+__device__ __forceinline__ int owned_row(int m) {
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    const int wb = (m & 1) ? (CTA_WARPS - 1 - w) : w;
+    return ((m * CTA_WARPS + wb) << 5) + l;
+}
+__device__ __forceinline__ int owned_rounds(int n) { return (n + CTA_THREADS - 1) / CTA_THREADS; }
+
 // c = max(#{x <= g_i(q)}, cmin) for outer row i; the search is confined to [lo, hi]
 __device__ __forceinline__ int count_row(const KernelParams& P, const Smem& S, double q, int i, int lo, int hi) {
     const double g = inner_bound(q, S.xs[i], P.w0, P.w1);
@@ -194,8 +205,10 @@ __device__ __forceinline__ int count_row(const KernelParams& P, const Smem& S, d
 __device__ __forceinline__ void count_rows(const KernelParams& P, const Smem& S, double q, u16* ctarget,
                                            const u16* slo, const u16* shi) {
     const int n = P.n;
-    for (int i = threadIdx.x; i < n; i += CTA_THREADS)
-        ctarget[i] = (u16)count_row(P, S, q, i, slo ? (int)slo[i] : 0, shi ? (int)shi[i] : n);
+    for (int m = 0; m < owned_rounds(n); ++m) {
+        const int i = owned_row(m);
+        if (i < n) ctarget[i] = (u16)count_row(P, S, q, i, slo ? (int)slo[i] : 0, shi ? (int)shi[i] : n);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -305,7 +318,9 @@ __device__ StripResult strip_pass(const KernelParams& P, const Smem& S, const Li
     double total = 0.0;
     unsigned cells = 0;
     bool poison = false;
-    for (int i = threadIdx.x; i < n; i += CTA_THREADS) {
+    for (int m = 0; m < owned_rounds(n); ++m) {
+        const int i = owned_row(m);
+        if (i >= n) continue;
         if (do_count) cnew[i] = (u16)count_row(P, S, q_new, i, slo ? (int)slo[i] : 0, shi ? (int)shi[i] : n);
         int s = ca ? (int)ca[i] : P.cmin;
         int e = (int)cb[i];
@@ -352,10 +367,12 @@ __device__ StripResult strip_pass(const KernelParams& P, const Smem& S, const Li
 template <int COPULA>
 __global__ void __launch_bounds__(CTA_THREADS, 2)
 solve_kernel(KernelParams P, const double* __restrict__ day_params, long long T, AlphaSet A,
-             unsigned* __restrict__ traj, double* __restrict__ mass_out, unsigned long long* __restrict__ cells_out) {
+             const int* __restrict__ order, unsigned* __restrict__ traj, double* __restrict__ mass_out,
+             unsigned long long* __restrict__ cells_out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const Smem S = carve(smem_raw, P.n);
-    const long long day = blockIdx.x;
+    // CTAs are dispatched in block-index order; `order` lists the days most expensive first (see order_key_kernel)
+    const long long day = order ? order[blockIdx.x] : blockIdx.x;
     const int stride = (P.marginal == 0) ? 2 : 2 * P.q;
     stage0<COPULA>(P, day_params + day * stride, S);
 
@@ -469,6 +486,34 @@ strip_mass_kernel(KernelParams P, const double* __restrict__ day_params, const d
         out[day] = s.mass;
         if (cells_out) cells_out[day] = s.cells;
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// launch order: the cost of a solve falls with the day's portfolio volatility (calm days end in bracket C,
+// whose strips cover ~4x more cells than bracket D's), so days are started in ascending order of a
+// variance proxy and the last CTAs of the launch are the cheap ones.  Ordering never changes results.
+// ---------------------------------------------------------------------------------------------
+__global__ void order_key_kernel(KernelParams P, const double* __restrict__ day_params, long long T, double rho_eff,
+                                 float* __restrict__ key, int* __restrict__ idx) {
+    const long long d = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (d >= T) return;
+    double v[2];
+    if (P.marginal == 0) {
+        v[0] = day_params[2 * d] * day_params[2 * d];
+        v[1] = day_params[2 * d + 1] * day_params[2 * d + 1];
+    } else {
+        for (int a = 0; a < 2; ++a) {
+            double acc = 0.0;
+            for (int s = 0; s < P.q; ++s) {
+                const double sg = P.sigma_states[a * P.q + s];
+                acc += day_params[(2 * d + a) * P.q + s] * sg * sg;
+            }
+            v[a] = acc;
+        }
+    }
+    const double var_p = P.w0 * P.w0 * v[0] + P.w1 * P.w1 * v[1] + 2.0 * rho_eff * P.w0 * P.w1 * sqrt(v[0] * v[1]);
+    key[d] = (float)fmax(var_p, 0.0);
+    idx[d] = (int)d;
 }
 
 // ---------------------------------------------------------------------------------------------
