@@ -35,6 +35,7 @@ struct cvar_plan {
     double* d_dx;
     double* d_sigma_states;
     double* d_tq_table;
+    double* d_logtab;
     // growable workspace of the *_host entry points
     void* d_ws;
     size_t ws_bytes;
@@ -387,6 +388,14 @@ int cvar_plan_create(const cvar_desc_t* desc, const double* x, const double* dx,
         cudaFree(d_err);
         std::memcpy(&p->tq_err, &bits, sizeof(double));
         kp.tq_table = p->d_tq_table;
+        // table-assisted log2 of the cell loop: constants scaled by -(nu+2)/2
+        constexpr double q1p[] = CVAR_LOG2_1P_POLY;
+        kp.negc = -0.5 * (desc->nu + 2.0);
+        for (int k = 0; k <= CVAR_LOG2_1P_POLY_DEG; ++k) kp.qc[k] = kp.negc * q1p[k];
+        PLAN_TRY(cudaMalloc(&p->d_logtab, sizeof(double) * LOGTAB_SIZE));
+        logtab_build_kernel<<<1, LOGTAB_SIZE, 0, p->stream>>>(kp.negc, p->d_logtab);
+        PLAN_TRY(cudaGetLastError());
+        kp.logtab = p->d_logtab;
     }
     PLAN_TRY(cudaStreamSynchronize(p->stream));
 
@@ -417,6 +426,7 @@ int cvar_plan_destroy(cvar_plan_t* p) {
     cudaFree(p->d_dx);
     cudaFree(p->d_sigma_states);
     cudaFree(p->d_tq_table);
+    cudaFree(p->d_logtab);
     cudaFree(p->d_ws);
     cudaFree(p->d_k);
     cudaFree(p->d_sched);

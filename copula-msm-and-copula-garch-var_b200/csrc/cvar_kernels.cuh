@@ -37,6 +37,9 @@ struct KernelParams {
     double g_out_scale;  // gaussian: sgn(rho) sqrt(log2e/(2(1-rho^2)))   student: rho/sqrt(nu(1-rho^2))
     double g_const;      // gaussian: (1-rho^2)^(-1/2)            student: Gamma-ratio / sqrt(1-rho^2)
     double tq_tail_lc;   // student: log of the leading tail coefficient
+    double negc;         // student: -(nu+2)/2, the exponent of the quadratic form
+    double qc[CVAR_LOG2_1P_POLY_DEG + 1];  // student: negc * coefficients of log2(1+f)/f
+    const double* logtab;  // student: negc * (-log2 r_i), LOGTAB_SIZE entries (global; staged to shared memory)
     const double* x;
     const double* dx;
     const double* sigma_states;  // [2][q] or nullptr
@@ -59,11 +62,12 @@ struct Smem {
     double* red;    // [2][CTA_WARPS]
     unsigned* redc; // [2][CTA_WARPS]
     int* live;      // [4]: dead-prefix / dead-suffix counts per axis
+    double* ltab;   // [LOGTAB_SIZE] student only
 };
 
 __host__ __device__ inline size_t smem_bytes_for(int n) {
     size_t npad = (size_t)((n + 3) & ~3);
-    return npad * 8 * 6 + npad * 2 * 3 + 2 * CTA_WARPS * 8 + 2 * CTA_WARPS * 4 + 16 + 64;
+    return npad * 8 * 6 + npad * 2 * 3 + 2 * CTA_WARPS * 8 + 2 * CTA_WARPS * 4 + 16 + 64 + LOGTAB_SIZE * 8;
 }
 
 __device__ __forceinline__ Smem carve(unsigned char* base, int n) {
@@ -82,6 +86,7 @@ __device__ __forceinline__ Smem carve(unsigned char* base, int n) {
     S.c[2] = h + 2 * npad;
     S.redc = reinterpret_cast<unsigned*>(h + 3 * npad);
     S.live = reinterpret_cast<int*>(S.redc + 2 * CTA_WARPS);
+    S.ltab = reinterpret_cast<double*>(S.live + 4 + 12);  // keeps 8-byte alignment: 2*npad*... + 64 + 64 bytes precede
     return S;
 }
 
@@ -92,6 +97,7 @@ template <int COPULA>
 __device__ void stage0(const KernelParams& P, const double* __restrict__ dayp, const Smem& S) {
     const int n = P.n, q = P.q;
     if (threadIdx.x < 4) S.live[threadIdx.x] = 0;
+    if (COPULA == 1 && threadIdx.x < LOGTAB_SIZE) S.ltab[threadIdx.x] = P.logtab[threadIdx.x];
     __syncthreads();
     const bool swap = (P.compat & 1u) != 0;
     for (int i = threadIdx.x; i < n; i += CTA_THREADS) {
@@ -224,24 +230,24 @@ struct Row<0> {  // Gaussian:  W = rowfac * 2^( l1[j] - (y1'[j] - m0)^2 )
         m0 = S.out0[i];
         fac = S.out1[i];
     }
-    __device__ __forceinline__ double cell(const KernelParams&, double a, double b) const {
+    __device__ __forceinline__ double cell(const KernelParams&, const Smem&, double a, double b) const {
         const double d = a - m0;
         return exp2_fast(fma(-d, d, b));
     }
 };
 
 template <>
-struct Row<1> {  // Student-t: W = rowfac * 2^( l1[j] - (nu+2)/2 * log2( c0 + (y1'[j] - m0)^2 ) )
+struct Row<1> {  // Student-t: W = rowfac * 2^( l1[j] - (nu+2)/2 * log2( c0 + (y1'[j] - m0)^2 ) ), table-assisted log2
     double m0, c0, fac;
     __device__ __forceinline__ void load(const KernelParams&, const Smem& S, int i) {
         m0 = S.out0[i];
         c0 = S.out1[i];
         fac = S.out2[i];
     }
-    __device__ __forceinline__ double cell(const KernelParams& P, double a, double b) const {
+    __device__ __forceinline__ double cell(const KernelParams& P, const Smem& S, double a, double b) const {
         const double d = a - m0;
-        const double t = fma(d, d, c0);
-        return exp2_fast(fma(-0.5 * (P.nu + 2.0), log2_fast(t), b));
+        const double t = fma(d, d, c0);  // >= 1
+        return exp2_fast(scaled_log2_plus(t, b, P.negc, P.qc, S.ltab));
     }
 };
 
@@ -257,7 +263,7 @@ struct Row<2> {  // Plackett (the reference's formula, plackett.py:66-69), u = r
         n1 = P.theta * eta * (1.0 - 2.0 * u);
         fac = S.out1[i];
     }
-    __device__ __forceinline__ double cell(const KernelParams&, double v, double a1) const {
+    __device__ __forceinline__ double cell(const KernelParams&, const Smem&, double v, double a1) const {
         const double num = fma(n1, v, n0);
         const double pp = fma(eta, v, p0);
         const double rr = fma(-eta, v, r0);
@@ -345,11 +351,11 @@ __device__ StripResult strip_pass(const KernelParams& P, const Smem& S, const Li
 #pragma unroll
             for (int c = 0; c < CELLS_IN_FLIGHT; ++c) v[c] = S.in[j + c];
 #pragma unroll
-            for (int c = 0; c < CELLS_IN_FLIGHT; ++c) acc[c] += row.cell(P, v[c].x, v[c].y);
+            for (int c = 0; c < CELLS_IN_FLIGHT; ++c) acc[c] += row.cell(P, S, v[c].x, v[c].y);
         }
         for (; j < e; ++j) {
             const double2 v = S.in[j];
-            acc[0] += row.cell(P, v.x, v.y);
+            acc[0] += row.cell(P, S, v.x, v.y);
         }
         double rowsum = acc[0];
 #pragma unroll

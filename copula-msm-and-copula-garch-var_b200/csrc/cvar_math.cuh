@@ -25,15 +25,15 @@ __constant__ double kExp2Coef[CVAR_EXP2_POLY_DEG + 1] = CVAR_EXP2_POLY;
 __constant__ double kAtanhCoef[CVAR_ATANH_POLY_DEG + 1] = CVAR_ATANH_POLY;
 
 // 2^t for finite t <= ~1000.  Results below 2^-1021 flush to ~1e-308 (never garbage).  Max relative
-// error ~2e-16 (degree-11 near-minimax on [-1/2, 1/2]).
+// error ~4e-16 (degree-10 near-minimax on [-1/2, 1/2]).
 __device__ __forceinline__ double exp2_fast(double t) {
     const double MAGIC = 6755399441055744.0;  // 1.5 * 2^52: adding it rounds t to the nearest integer
     const double kf = __dadd_rn(t, MAGIC);
     int k = __double2loint(kf);
     const double r = __dadd_rn(t, -__dadd_rn(kf, -MAGIC));  // r in [-1/2, 1/2], exact
-    double p = kExp2Coef[11];
+    double p = kExp2Coef[CVAR_EXP2_POLY_DEG];
 #pragma unroll
-    for (int i = 10; i >= 0; --i) p = fma(p, r, kExp2Coef[i]);
+    for (int i = CVAR_EXP2_POLY_DEG - 1; i >= 0; --i) p = fma(p, r, kExp2Coef[i]);
     k = max(k, -1021);
     return __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
 }
@@ -69,6 +69,45 @@ __device__ __forceinline__ double log2_fast(double t) {
     for (int i = 5; i >= 0; --i) p = fma(p, z, kAtanhCoef[i]);
     const double sc = s * CVAR_TWO_OVER_LN2;
     return fma(sc, z * p, sc) + (double)e;
+}
+
+// ----- table-assisted  c * log2(t)  for the Student-t cell -----------------------------------------
+// t = 2^e * m, m in [1, 2).  The top 7 mantissa bits select an interval; its midpoint reciprocal r_i comes
+// from MUFU.RCP64H (deterministic, so the table built with the same instruction matches it exactly) and
+// f = m * r_i - 1 is exact in one DFMA with |f| <= 2^-8.  Then
+//     c * log2(t) = c * e + c * (-log2 r_i) + f * (c * Q(f)),   Q(f) = log2(1+f)/f  (degree 5)
+// with c folded into the table (LOGTAB_SIZE doubles in shared memory) and into the polynomial (plan constants).
+constexpr int LOGTAB_BITS = 7;
+constexpr int LOGTAB_SIZE = 1 << LOGTAB_BITS;
+
+__device__ __forceinline__ double logtab_recip(int idx) {
+    // reciprocal of the midpoint of mantissa interval idx, exactly as the cell loop obtains it
+    const double mid = __hiloint2double(0x3ff00000 | (idx << (20 - LOGTAB_BITS)) | (1 << (19 - LOGTAB_BITS)), 0);
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(mid));
+    return r;
+}
+
+__global__ void logtab_build_kernel(double c, double* __restrict__ tab) {
+    const int i = threadIdx.x;
+    if (i < LOGTAB_SIZE) tab[i] = -c * log2(logtab_recip(i));
+}
+
+// returns c*log2(t) + b for positive normal t;  qc[k] = c * (coefficients of Q), tab = c * (-log2 r_i)
+__device__ __forceinline__ double scaled_log2_plus(double t, double b, double c, const double* __restrict__ qc,
+                                                   const double* __restrict__ tab) {
+    const int hi = __double2hiint(t);
+    const int e = (hi >> 20) - 1023;
+    const int idx = (hi >> (20 - LOGTAB_BITS)) & (LOGTAB_SIZE - 1);
+    double r = logtab_recip(idx);
+    r = __hiloint2double(__double2hiint(r) - (e << 20), 0);  // r_i * 2^-e (the seed's low word is zero)
+    const double f = fma(t, r, -1.0);
+    double base = fma(c, (double)e, b);
+    base += tab[idx];
+    double q = qc[CVAR_LOG2_1P_POLY_DEG];
+#pragma unroll
+    for (int k = CVAR_LOG2_1P_POLY_DEG - 1; k >= 0; --k) q = fma(q, f, qc[k]);
+    return fma(f, q, base);
 }
 
 // ---------------------------------------------------------------------------------------------

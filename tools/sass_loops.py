@@ -28,7 +28,8 @@ for i, (a, txt) in enumerate(ins):
         if tgt <= a and tgt in addr_index:
             loops.append((addr_index[tgt], i))
 FP64 = ("DFMA", "DADD", "DMUL", "DSETP", "DMNMX")
-for s, e in sorted(loops, key=lambda t: t[0] - t[1])[:12]:
+order = sorted(loops, key=lambda t: t[0] - t[1]) if len(sys.argv) < 3 else sorted(loops, key=lambda t: t[1] - t[0])
+for s, e in order[:int(sys.argv[2]) if len(sys.argv) > 2 else 12]:
     ops = Counter()
     for _, txt in ins[s:e + 1]:
         t = txt.split()
