@@ -36,6 +36,9 @@ struct cvar_plan {
     double* d_sigma_states;
     double* d_tq_table;
     double* d_logtab;
+    double* d_exptab;
+    double* d_state_cdf;
+    double* d_state_pdf;
     // growable workspace of the *_host entry points
     void* d_ws;
     size_t ws_bytes;
@@ -373,6 +376,22 @@ int cvar_plan_create(const cvar_desc_t* desc, const double* x, const double* dx,
     kp.x = p->d_x;
     kp.dx = p->d_dx;
     kp.sigma_states = p->d_sigma_states;
+    if (desc->copula != CVAR_COPULA_PLACKETT) {
+        PLAN_TRY(cudaMalloc(&p->d_exptab, sizeof(double) * EXPTAB_SIZE));
+        exptab_build_kernel<<<1, EXPTAB_SIZE, 0, p->stream>>>(p->d_exptab);
+        PLAN_TRY(cudaGetLastError());
+        kp.exptab = p->d_exptab;
+    }
+    if (desc->marginal == CVAR_MARGINAL_MIXTURE) {
+        const size_t cnt = (size_t)2 * q * n;
+        PLAN_TRY(cudaMalloc(&p->d_state_cdf, sizeof(double) * cnt));
+        PLAN_TRY(cudaMalloc(&p->d_state_pdf, sizeof(double) * cnt));
+        state_table_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, p->stream>>>(n, q, p->d_x, p->d_sigma_states,
+                                                                                p->d_state_cdf, p->d_state_pdf);
+        PLAN_TRY(cudaGetLastError());
+        kp.state_cdf = p->d_state_cdf;
+        kp.state_pdf = p->d_state_pdf;
+    }
     if (desc->copula == CVAR_COPULA_STUDENT) {
         PLAN_TRY(cudaMalloc(&p->d_tq_table, sizeof(double) * TQ_TABLE_DOUBLES));
         tq_table_build_kernel<<<TQ_INTERVALS, 32, 0, p->stream>>>(desc->nu, p->d_tq_table);
@@ -427,6 +446,9 @@ int cvar_plan_destroy(cvar_plan_t* p) {
     cudaFree(p->d_sigma_states);
     cudaFree(p->d_tq_table);
     cudaFree(p->d_logtab);
+    cudaFree(p->d_exptab);
+    cudaFree(p->d_state_cdf);
+    cudaFree(p->d_state_pdf);
     cudaFree(p->d_ws);
     cudaFree(p->d_k);
     cudaFree(p->d_sched);
@@ -583,7 +605,7 @@ int cvar_test_special_host(cvar_plan_t* p, int32_t which, const double* in, int6
     double* d_out = (double*)((char*)p->d_ws + b);
     CU_TRY(cudaMemcpyAsync(d_in, in, sizeof(double) * count, cudaMemcpyHostToDevice, p->stream));
     special_kernel<<<(unsigned)((count + 127) / 128), 128, 0, p->stream>>>(which, p->desc.nu, p->d_tq_table, p->kp.tq_tail_lc,
-                                                                          d_in, (long long)count, d_out);
+                                                                          p->d_exptab, d_in, (long long)count, d_out);
     CU_TRY(cudaGetLastError());
     CU_TRY(cudaMemcpyAsync(out, d_out, sizeof(double) * count, cudaMemcpyDeviceToHost, p->stream));
     CU_TRY(cudaStreamSynchronize(p->stream));

@@ -40,10 +40,13 @@ struct KernelParams {
     double negc;         // student: -(nu+2)/2, the exponent of the quadratic form
     double qc[CVAR_LOG2_1P_POLY_DEG + 1];  // student: negc * coefficients of log2(1+f)/f
     const double* logtab;  // student: negc * (-log2 r_i), LOGTAB_SIZE entries (global; staged to shared memory)
+    const double* exptab;  // gaussian / student: 2^(i/256), EXPTAB_SIZE entries (global; staged to shared memory)
     const double* x;
     const double* dx;
     const double* sigma_states;  // [2][q] or nullptr
     const double* tq_table;      // student only
+    const double* state_cdf;     // mixture: Phi(x_i / sigma_{a,s}), [2][q][n]
+    const double* state_pdf;     // mixture: N(x_i; 0, sigma_{a,s}), [2][q][n]
 };
 
 struct AlphaSet {
@@ -63,11 +66,12 @@ struct Smem {
     unsigned* redc; // [2][CTA_WARPS]
     int* live;      // [4]: dead-prefix / dead-suffix counts per axis
     double* ltab;   // [LOGTAB_SIZE] student only
+    double* etab;   // [EXPTAB_SIZE] gaussian / student
 };
 
 __host__ __device__ inline size_t smem_bytes_for(int n) {
     size_t npad = (size_t)((n + 3) & ~3);
-    return npad * 8 * 6 + npad * 2 * 3 + 2 * CTA_WARPS * 8 + 2 * CTA_WARPS * 4 + 16 + 64 + LOGTAB_SIZE * 8;
+    return npad * 8 * 6 + npad * 2 * 3 + 2 * CTA_WARPS * 8 + 2 * CTA_WARPS * 4 + 16 + 64 + LOGTAB_SIZE * 8 + EXPTAB_SIZE * 8;
 }
 
 __device__ __forceinline__ Smem carve(unsigned char* base, int n) {
@@ -86,7 +90,8 @@ __device__ __forceinline__ Smem carve(unsigned char* base, int n) {
     S.c[2] = h + 2 * npad;
     S.redc = reinterpret_cast<unsigned*>(h + 3 * npad);
     S.live = reinterpret_cast<int*>(S.redc + 2 * CTA_WARPS);
-    S.ltab = reinterpret_cast<double*>(S.live + 4 + 12);  // keeps 8-byte alignment: 2*npad*... + 64 + 64 bytes precede
+    S.ltab = reinterpret_cast<double*>(S.live + 4 + 12);  // 64 bytes after `live`: stays 8-byte aligned
+    S.etab = S.ltab + LOGTAB_SIZE;
     return S;
 }
 
@@ -98,6 +103,8 @@ __device__ void stage0(const KernelParams& P, const double* __restrict__ dayp, c
     const int n = P.n, q = P.q;
     if (threadIdx.x < 4) S.live[threadIdx.x] = 0;
     if (COPULA == 1 && threadIdx.x < LOGTAB_SIZE) S.ltab[threadIdx.x] = P.logtab[threadIdx.x];
+    if (COPULA != 2)
+        for (int k = threadIdx.x; k < EXPTAB_SIZE; k += CTA_THREADS) S.etab[k] = P.exptab[k];
     __syncthreads();
     const bool swap = (P.compat & 1u) != 0;
     for (int i = threadIdx.x; i < n; i += CTA_THREADS) {
@@ -115,18 +122,20 @@ __device__ void stage0(const KernelParams& P, const double* __restrict__ dayp, c
             }
         } else {
             // msm_integration_function.py:32-36 (cdf mixture) and create_grids.py:121,143 (pdf mixture
-            // with the vol states of the OTHER asset when the Q3 compat bit is set)
+            // with the vol states of the OTHER asset when the Q3 compat bit is set).  The vol states are run
+            // constants, so Phi(x_i / sigma_{a,s}) and N(x_i; 0, sigma_{a,s}) do not depend on the day: they
+            // are tabulated once per plan (state_table_kernel) and a day only forms the two probability-
+            // weighted sums per axis point -- q FMAs instead of q erf + q exp evaluations.
 #pragma unroll
             for (int d = 0; d < 2; ++d) {
                 double su = 0.0, sa = 0.0;
                 const double* pr = dayp + d * q;
-                const double* sg_own = P.sigma_states + d * q;
-                const double* sg_pdf = P.sigma_states + (swap ? (1 - d) : d) * q;
+                const double* cdf_t = P.state_cdf + (size_t)d * q * n + i;
+                const double* pdf_t = P.state_pdf + (size_t)(swap ? (1 - d) : d) * q * n + i;
                 for (int s = 0; s < q; ++s) {
                     const double p = pr[s];
-                    su += p * phi_via_erf(__ddiv_rn(xi, sg_own[s]));
-                    const double zz = __ddiv_rn(xi, sg_pdf[s]);
-                    sa += p * (exp(-0.5 * zz * zz) / (2.5066282746310002 * sg_pdf[s]));
+                    su += p * cdf_t[(size_t)s * n];
+                    sa += p * pdf_t[(size_t)s * n];
                 }
                 u[d] = su;
                 a[d] = dxi * sa;
@@ -167,6 +176,19 @@ __device__ void stage0(const KernelParams& P, const double* __restrict__ dayp, c
         }
     }
     __syncthreads();
+}
+
+// per-plan tables of the mixture marginals: one thread per (asset, state, axis point)
+__global__ void state_table_kernel(int n, int q, const double* __restrict__ x, const double* __restrict__ sigma_states,
+                                   double* __restrict__ cdf, double* __restrict__ pdf) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= 2LL * q * n) return;
+    const int i = (int)(idx % n);
+    const int as = (int)(idx / n);  // a * q + s
+    const double sg = sigma_states[as];
+    const double z = __ddiv_rn(x[i], sg);
+    cdf[idx] = phi_via_erf(z);                                        // utils/utils.py:17-22
+    pdf[idx] = exp(-0.5 * z * z) / (2.5066282746310002 * sg);         // msm_estimation.py:328
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -230,9 +252,9 @@ struct Row<0> {  // Gaussian:  W = rowfac * 2^( l1[j] - (y1'[j] - m0)^2 )
         m0 = S.out0[i];
         fac = S.out1[i];
     }
-    __device__ __forceinline__ double cell(const KernelParams&, const Smem&, double a, double b) const {
+    __device__ __forceinline__ double cell(const KernelParams&, const Smem& S, double a, double b) const {
         const double d = a - m0;
-        return exp2_fast(fma(-d, d, b));
+        return exp2_tab(fma(-d, d, b), S.etab);
     }
 };
 
@@ -247,7 +269,7 @@ struct Row<1> {  // Student-t: W = rowfac * 2^( l1[j] - (nu+2)/2 * log2( c0 + (y
     __device__ __forceinline__ double cell(const KernelParams& P, const Smem& S, double a, double b) const {
         const double d = a - m0;
         const double t = fma(d, d, c0);  // >= 1
-        return exp2_fast(scaled_log2_plus(t, b, P.negc, P.qc, S.ltab));
+        return exp2_tab(scaled_log2_plus(t, b, P.negc, P.qc, S.ltab), S.etab);
     }
 };
 
@@ -595,7 +617,8 @@ __global__ void finalize_apply_kernel(FinalizeParams F, const unsigned* __restri
 // special-function test kernel
 // ---------------------------------------------------------------------------------------------
 __global__ void special_kernel(int which, double nu, const double* __restrict__ table, double tail_lc,
-                               const double* __restrict__ in, long long count, double* __restrict__ out) {
+                               const double* __restrict__ exptab, const double* __restrict__ in, long long count,
+                               double* __restrict__ out) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= count) return;
     const double v = in[i];
@@ -608,6 +631,7 @@ __global__ void special_kernel(int which, double nu, const double* __restrict__ 
         case 4: r = phi_via_erf(v); break;
         case 5: r = normcdfinv(v); break;
         case 6: r = rcp_fast(v); break;
+        case 7: r = exptab ? exp2_tab(v, exptab) : NAN; break;
         default: r = NAN;
     }
     out[i] = r;

@@ -38,6 +38,30 @@ __device__ __forceinline__ double exp2_fast(double t) {
     return __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
 }
 
+// 2^t through a 256-entry table of 2^(i/256) (shared memory) and a degree-4 polynomial on |r| <= 2^-9:
+// 8 FP64 instructions instead of 13.  Same argument contract as exp2_fast.
+constexpr int EXPTAB_BITS = 8;
+constexpr int EXPTAB_SIZE = 1 << EXPTAB_BITS;
+__constant__ double kExp2SmallCoef[CVAR_EXP2_SMALL_POLY_DEG + 1] = CVAR_EXP2_SMALL_POLY;
+
+__global__ void exptab_build_kernel(double* __restrict__ tab) {
+    const int i = threadIdx.x;
+    if (i < EXPTAB_SIZE) tab[i] = exp2((double)i / EXPTAB_SIZE);
+}
+
+__device__ __forceinline__ double exp2_tab(double t, const double* __restrict__ tab) {
+    const double MAGIC = 6755399441055744.0 / EXPTAB_SIZE;  // rounds t to the nearest multiple of 2^-8
+    const double kf = __dadd_rn(t, MAGIC);
+    const int k256 = __double2loint(kf);                     // round(t * 256), two's complement
+    const double r = __dadd_rn(t, -__dadd_rn(kf, -MAGIC));   // |r| <= 2^-9, exact
+    double p = kExp2SmallCoef[CVAR_EXP2_SMALL_POLY_DEG];
+#pragma unroll
+    for (int i = CVAR_EXP2_SMALL_POLY_DEG - 1; i >= 0; --i) p = fma(p, r, kExp2SmallCoef[i]);
+    const double v = tab[k256 & (EXPTAB_SIZE - 1)] * p;      // in [1, 2.01)
+    const int k = max(k256 >> EXPTAB_BITS, -1021);
+    return __hiloint2double(__double2hiint(v) + (k << 20), __double2loint(v));
+}
+
 // 1/a for finite normal a: MUFU.RCP64H seed (2^-23) + two Newton steps on the FP64 pipe.
 __device__ __forceinline__ double rcp_fast(double a) {
     double r;

@@ -81,6 +81,10 @@ def test_exp2_log2_rcp_primitives(backend):
         l = plan.special(3, x)
         r = plan.special(6, x)
         tiny = plan.special(2, np.array([-1100.0, -5000.0]))
+        et = plan.special(7, t)                      # table-assisted variant used by the Gaussian / Student cells
+        tiny_t = plan.special(7, np.array([-1100.0, -5000.0]))
+    assert np.max(np.abs(et / np.exp2(t) - 1)) < 7e-16
+    assert np.all(tiny_t >= 0) and np.all(tiny_t < 1e-300)
     assert np.max(np.abs(e / np.exp2(t) - 1)) < 7e-16
     assert np.max(np.abs(l - np.log2(x)) / np.maximum(np.abs(np.log2(x)), 1e-3)) < 6e-16
     assert np.max(np.abs(r * x - 1)) < 3e-16
