@@ -26,6 +26,7 @@ struct cvar_plan {
     int device;
     int sm_count;
     int ctas_per_sm;
+    int cta_threads;
     size_t smem_bytes;
     double tq_err;
     double last_kernel_ms;
@@ -149,7 +150,7 @@ int launch_solve(cvar_plan* p, const double* d_day, int64_t T, const AlphaSet& A
     const int* order = nullptr;
     int rc = make_order(p, d_day, T, st, &order);
     if (rc) return rc;
-    dim3 grid((unsigned)T), block(CTA_THREADS);
+    dim3 grid((unsigned)T), block(p->cta_threads);
     switch (p->desc.copula) {
         case CVAR_COPULA_GAUSSIAN:
             solve_kernel<0><<<grid, block, p->smem_bytes, st>>>(p->kp, d_day, (long long)T, A, order, d_traj, d_mass, d_cells);
@@ -166,7 +167,7 @@ int launch_solve(cvar_plan* p, const double* d_day, int64_t T, const AlphaSet& A
 int launch_strip(cvar_plan* p, const double* d_day, int64_t T, const double* d_bounds, double* d_out,
                  unsigned long long* d_cells, cudaStream_t st) {
     if (T == 0) return 0;
-    dim3 grid((unsigned)T), block(CTA_THREADS);
+    dim3 grid((unsigned)T), block(p->cta_threads);
     switch (p->desc.copula) {
         case CVAR_COPULA_GAUSSIAN:
             strip_mass_kernel<0><<<grid, block, p->smem_bytes, st>>>(p->kp, d_day, d_bounds, d_out, d_cells);
@@ -426,10 +427,15 @@ int cvar_plan_create(const cvar_desc_t* desc, const double* x, const double* dx,
     PLAN_TRY((cudaError_t)set_smem(strip_mass_kernel<1>, p->smem_bytes));
     PLAN_TRY((cudaError_t)set_smem(strip_mass_kernel<2>, p->smem_bytes));
     int occ = 0;
-    switch (desc->copula) {
-        case CVAR_COPULA_GAUSSIAN: PLAN_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, solve_kernel<0>, CTA_THREADS, p->smem_bytes)); break;
-        case CVAR_COPULA_STUDENT: PLAN_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, solve_kernel<1>, CTA_THREADS, p->smem_bytes)); break;
-        default: PLAN_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, solve_kernel<2>, CTA_THREADS, p->smem_bytes));
+    p->cta_threads = CTA_THREADS_SMALL;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        switch (desc->copula) {
+            case CVAR_COPULA_GAUSSIAN: PLAN_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, solve_kernel<0>, p->cta_threads, p->smem_bytes)); break;
+            case CVAR_COPULA_STUDENT: PLAN_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, solve_kernel<1>, p->cta_threads, p->smem_bytes)); break;
+            default: PLAN_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, solve_kernel<2>, p->cta_threads, p->smem_bytes));
+        }
+        if (occ >= 2 || attempt == 1) break;
+        p->cta_threads = CTA_THREADS_LARGE;   // only one CTA fits an SM: give it 16 warps
     }
     p->ctas_per_sm = occ;
 #undef PLAN_TRY
@@ -465,7 +471,7 @@ int cvar_plan_get_info(const cvar_plan_t* p, cvar_plan_info_t* info) {
     info->sm_count = p->sm_count;
     info->max_iter = p->kp.max_iter;
     info->ctas_per_sm = p->ctas_per_sm;
-    info->threads_per_cta = CTA_THREADS;
+    info->threads_per_cta = p->cta_threads;
     info->smem_bytes_per_cta = (int32_t)p->smem_bytes;
     info->tq_table_max_rel_err = p->tq_err;
     info->last_kernel_ms = p->last_kernel_ms;

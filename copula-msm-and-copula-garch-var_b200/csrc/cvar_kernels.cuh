@@ -19,9 +19,25 @@
 
 namespace cvar {
 
-constexpr int CTA_THREADS = 256;
-constexpr int CTA_WARPS = CTA_THREADS / 32;
-constexpr int CELLS_IN_FLIGHT = 4;  // independent cells per thread per loop trip (FP64 latency hiding)
+// CTA size is chosen per plan: 256 threads when two CTAs fit one SM's shared memory (n <= ~2300), otherwise
+// one CTA of 512 threads per SM, so that an SM always has 16 warps of row walkers resident.
+constexpr int CTA_THREADS_SMALL = 256;
+constexpr int CTA_THREADS_LARGE = 512;
+constexpr int MAX_CTA_WARPS = CTA_THREADS_LARGE / 32;
+// independent cells per thread per loop trip (FP64 latency hiding); the cheap cells need more of them
+#ifndef CVAR_CIF_GAUSSIAN
+#define CVAR_CIF_GAUSSIAN 8
+#endif
+#ifndef CVAR_CIF_STUDENT
+#define CVAR_CIF_STUDENT 4
+#endif
+#ifndef CVAR_CIF_PLACKETT
+#define CVAR_CIF_PLACKETT 8
+#endif
+template <int COPULA>
+struct CellsInFlight {
+    static constexpr int value = COPULA == 0 ? CVAR_CIF_GAUSSIAN : (COPULA == 1 ? CVAR_CIF_STUDENT : CVAR_CIF_PLACKETT);
+};
 
 typedef unsigned short u16;
 
@@ -62,8 +78,8 @@ struct Smem {
     double* out1;   // [n]
     double* out2;   // [n]
     u16* c[3];      // [n] each: inner index bounds per outer row
-    double* red;    // [2][CTA_WARPS]
-    unsigned* redc; // [2][CTA_WARPS]
+    double* red;    // [2][MAX_CTA_WARPS]
+    unsigned* redc; // [2][MAX_CTA_WARPS]
     int* live;      // [4]: dead-prefix / dead-suffix counts per axis
     double* ltab;   // [LOGTAB_SIZE] student only
     double* etab;   // [EXPTAB_SIZE] gaussian / student
@@ -71,7 +87,7 @@ struct Smem {
 
 __host__ __device__ inline size_t smem_bytes_for(int n) {
     size_t npad = (size_t)((n + 3) & ~3);
-    return npad * 8 * 6 + npad * 2 * 3 + 2 * CTA_WARPS * 8 + 2 * CTA_WARPS * 4 + 16 + 64 + LOGTAB_SIZE * 8 + EXPTAB_SIZE * 8;
+    return npad * 8 * 6 + npad * 2 * 3 + 2 * MAX_CTA_WARPS * 8 + 2 * MAX_CTA_WARPS * 4 + 16 + 64 + LOGTAB_SIZE * 8 + EXPTAB_SIZE * 8;
 }
 
 __device__ __forceinline__ Smem carve(unsigned char* base, int n) {
@@ -84,12 +100,12 @@ __device__ __forceinline__ Smem carve(unsigned char* base, int n) {
     S.out1 = d + 4 * npad;
     S.out2 = d + 5 * npad;
     S.red = d + 6 * npad;
-    u16* h = reinterpret_cast<u16*>(S.red + 2 * CTA_WARPS);
+    u16* h = reinterpret_cast<u16*>(S.red + 2 * MAX_CTA_WARPS);
     S.c[0] = h;
     S.c[1] = h + npad;
     S.c[2] = h + 2 * npad;
     S.redc = reinterpret_cast<unsigned*>(h + 3 * npad);
-    S.live = reinterpret_cast<int*>(S.redc + 2 * CTA_WARPS);
+    S.live = reinterpret_cast<int*>(S.redc + 2 * MAX_CTA_WARPS);
     S.ltab = reinterpret_cast<double*>(S.live + 4 + 12);  // 64 bytes after `live`: stays 8-byte aligned
     S.etab = S.ltab + LOGTAB_SIZE;
     return S;
@@ -104,10 +120,10 @@ __device__ void stage0(const KernelParams& P, const double* __restrict__ dayp, c
     if (threadIdx.x < 4) S.live[threadIdx.x] = 0;
     if (COPULA == 1 && threadIdx.x < LOGTAB_SIZE) S.ltab[threadIdx.x] = P.logtab[threadIdx.x];
     if (COPULA != 2)
-        for (int k = threadIdx.x; k < EXPTAB_SIZE; k += CTA_THREADS) S.etab[k] = P.exptab[k];
+        for (int k = threadIdx.x; k < EXPTAB_SIZE; k += blockDim.x) S.etab[k] = P.exptab[k];
     __syncthreads();
     const bool swap = (P.compat & 1u) != 0;
-    for (int i = threadIdx.x; i < n; i += CTA_THREADS) {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
         const double xi = P.x[i], dxi = P.dx[i];
         S.xs[i] = xi;
         double u[2], a[2];
@@ -211,16 +227,17 @@ __device__ __forceinline__ int count_le(const double* __restrict__ xs, double g,
 }
 
 // Row ownership.  Rows are dealt to warps in blocks of 32 (lane = row within the block, so adjacent lanes walk
-// adjacent rows); the block-to-warp order alternates direction every round (0..7, 7..0, 0..7, ...) because
+// adjacent rows); the block-to-warp order alternates direction every round (0..W-1, W-1..0, ...) because
 // the strip length falls off monotonically with the row index and a fixed order would always hand warp 0
 // the longest rows.  The mapping is fixed for the whole solve: a thread only ever touches its own rows'
 // boundary entries, which is why no barrier separates the boundary search from the cell walk.
 __device__ __forceinline__ int owned_row(int m) {
     const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-    const int wb = (m & 1) ? (CTA_WARPS - 1 - w) : w;
-    return ((m * CTA_WARPS + wb) << 5) + l;
+    const int nw = blockDim.x >> 5;
+    const int wb = (m & 1) ? (nw - 1 - w) : w;
+    return ((m * nw + wb) << 5) + l;
 }
-__device__ __forceinline__ int owned_rounds(int n) { return (n + CTA_THREADS - 1) / CTA_THREADS; }
+__device__ __forceinline__ int owned_rounds(int n) { return (n + blockDim.x - 1) / blockDim.x; }
 
 // c = max(#{x <= g_i(q)}, cmin) for outer row i; the search is confined to [lo, hi]
 __device__ __forceinline__ int count_row(const KernelParams& P, const Smem& S, double q, int i, int lo, int hi) {
@@ -229,7 +246,7 @@ __device__ __forceinline__ int count_row(const KernelParams& P, const Smem& S, d
     return max(count_le(S.xs, g, lo, hi), P.cmin);
 }
 
-// ctarget[i] = count_row(q) for every outer row (thread t owns rows t, t + CTA_THREADS, ...)
+// ctarget[i] = count_row(q) for every outer row this thread owns
 __device__ __forceinline__ void count_rows(const KernelParams& P, const Smem& S, double q, u16* ctarget,
                                            const u16* slo, const u16* shi) {
     const int n = P.n;
@@ -311,17 +328,17 @@ __device__ __forceinline__ StripResult block_reduce(const Smem& S, int& parity, 
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     cells = __reduce_add_sync(0xffffffffu, cells);
     if (lane == 0) {
-        S.red[parity * CTA_WARPS + warp] = v;
-        S.redc[parity * CTA_WARPS + warp] = cells;
+        S.red[parity * MAX_CTA_WARPS + warp] = v;
+        S.redc[parity * MAX_CTA_WARPS + warp] = cells;
     }
     const int anyp = __syncthreads_or(poison ? 1 : 0);
     StripResult r;
     r.mass = 0.0;
     r.cells = 0;
-#pragma unroll
-    for (int w = 0; w < CTA_WARPS; ++w) {
-        r.mass += S.red[parity * CTA_WARPS + w];
-        r.cells += S.redc[parity * CTA_WARPS + w];
+    const int nw = blockDim.x >> 5;
+    for (int w = 0; w < nw; ++w) {   // fixed order: the sum does not depend on scheduling
+        r.mass += S.red[parity * MAX_CTA_WARPS + w];
+        r.cells += S.redc[parity * MAX_CTA_WARPS + w];
     }
     r.poisoned = anyp != 0;
     parity ^= 1;
@@ -330,7 +347,7 @@ __device__ __forceinline__ StripResult block_reduce(const Smem& S, int& parity, 
 
 // One strip of the bisection.
 //
-// Thread t owns outer rows t, t + CTA_THREADS, ... for the whole solve: it finds the row's new boundary
+// Every thread owns a fixed set of outer rows (owned_row) for the whole solve: it finds the row's new boundary
 // index by an exact binary search (when q_new is given), then walks the row's cells [a, b) itself with
 // CELLS_IN_FLIGHT independent cells per trip.  Adjacent lanes own adjacent rows, whose ranges are shifted
 // by about one column, so the 16-byte shared-memory loads of a warp fall on consecutive addresses.
@@ -342,6 +359,7 @@ template <int COPULA>
 __device__ StripResult strip_pass(const KernelParams& P, const Smem& S, const Live& L, int& parity, bool do_count,
                                   double q_new, u16* cnew, const u16* slo, const u16* shi, const u16* ca,
                                   const u16* cb, bool poison_mode) {
+    constexpr int CELLS_IN_FLIGHT = CellsInFlight<COPULA>::value;
     const int n = P.n;
     double total = 0.0;
     unsigned cells = 0;
@@ -349,7 +367,14 @@ __device__ StripResult strip_pass(const KernelParams& P, const Smem& S, const Li
     for (int m = 0; m < owned_rounds(n); ++m) {
         const int i = owned_row(m);
         if (i >= n) continue;
-        if (do_count) cnew[i] = (u16)count_row(P, S, q_new, i, slo ? (int)slo[i] : 0, shi ? (int)shi[i] : n);
+        if (do_count) {
+            const int lo = slo ? (int)slo[i] : 0, hi = shi ? (int)shi[i] : n;
+            if (slo && shi && lo == hi) {   // no grid point of this row between the bracket ends: nothing can move
+                cnew[i] = (u16)lo;
+                continue;
+            }
+            cnew[i] = (u16)count_row(P, S, q_new, i, lo, hi);
+        }
         int s = ca ? (int)ca[i] : P.cmin;
         int e = (int)cb[i];
         if (e <= s) continue;
@@ -393,7 +418,7 @@ __device__ StripResult strip_pass(const KernelParams& P, const Smem& S, const Li
 // the solve kernel
 // ---------------------------------------------------------------------------------------------
 template <int COPULA>
-__global__ void __launch_bounds__(CTA_THREADS, 2)
+__global__ void __launch_bounds__(CTA_THREADS_LARGE, 1)
 solve_kernel(KernelParams P, const double* __restrict__ day_params, long long T, AlphaSet A,
              const int* __restrict__ order, unsigned* __restrict__ traj, double* __restrict__ mass_out,
              unsigned long long* __restrict__ cells_out) {
@@ -489,7 +514,7 @@ solve_kernel(KernelParams P, const double* __restrict__ day_params, long long T,
 // strip-mass kernel (parity seam for compute_integral)
 // ---------------------------------------------------------------------------------------------
 template <int COPULA>
-__global__ void __launch_bounds__(CTA_THREADS, 2)
+__global__ void __launch_bounds__(CTA_THREADS_LARGE, 1)
 strip_mass_kernel(KernelParams P, const double* __restrict__ day_params, const double* __restrict__ bounds,
                   double* __restrict__ out, unsigned long long* __restrict__ cells_out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
