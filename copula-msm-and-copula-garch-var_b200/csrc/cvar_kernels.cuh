@@ -41,6 +41,12 @@ struct CellsInFlight {
 
 typedef unsigned short u16;
 
+// Alpha fusion: the alphas of a day walk the same first strips (F(first), the second probe, the first
+// bisection steps while their decisions agree).  A strip is a pure function of its (lo, hi) pair, so the first
+// MEMO_PER_ALPHA strips of every alpha are remembered and later alphas reuse the mass instead of re-integrating.
+constexpr int MEMO_SIZE = 32;
+constexpr int MEMO_PER_ALPHA = 7;
+
 struct KernelParams {
     int copula, marginal, n, q;
     unsigned compat;
@@ -83,11 +89,12 @@ struct Smem {
     int* live;      // [4]: dead-prefix / dead-suffix counts per axis
     double* ltab;   // [LOGTAB_SIZE] student only
     double* etab;   // [EXPTAB_SIZE] gaussian / student
+    double* memo;   // [MEMO_SIZE][4]: (lo, hi, mass, cells) of strips already integrated for an earlier alpha
 };
 
 __host__ __device__ inline size_t smem_bytes_for(int n) {
     size_t npad = (size_t)((n + 3) & ~3);
-    return npad * 8 * 6 + npad * 2 * 3 + 2 * MAX_CTA_WARPS * 8 + 2 * MAX_CTA_WARPS * 4 + 16 + 64 + LOGTAB_SIZE * 8 + EXPTAB_SIZE * 8;
+    return npad * 8 * 6 + npad * 2 * 3 + 2 * MAX_CTA_WARPS * 8 + 2 * MAX_CTA_WARPS * 4 + 16 + 64 + LOGTAB_SIZE * 8 + EXPTAB_SIZE * 8 + MEMO_SIZE * 4 * 8;
 }
 
 __device__ __forceinline__ Smem carve(unsigned char* base, int n) {
@@ -108,6 +115,7 @@ __device__ __forceinline__ Smem carve(unsigned char* base, int n) {
     S.live = reinterpret_cast<int*>(S.redc + 2 * MAX_CTA_WARPS);
     S.ltab = reinterpret_cast<double*>(S.live + 4 + 12);  // 64 bytes after `live`: stays 8-byte aligned
     S.etab = S.ltab + LOGTAB_SIZE;
+    S.memo = S.etab + EXPTAB_SIZE;
     return S;
 }
 
@@ -414,6 +422,39 @@ __device__ StripResult strip_pass(const KernelParams& P, const Smem& S, const Li
     return r;
 }
 
+// strip_pass with reuse across the alphas of a day.  `memo_n` (uniform across the CTA) counts the entries written
+// so far (by thread 0, right after a strip's reduction); only the first `memo_visible` of them -- those of
+// earlier alphas, published by the barrier at the top of the alpha loop -- are searched.
+template <int COPULA>
+__device__ __forceinline__ StripResult strip_memo(const KernelParams& P, const Smem& S, const Live& L, int& parity,
+                                                  bool use_memo, bool remember, int memo_visible, int& memo_n,
+                                                  double a, double b,
+                                                  double q_new, u16* cnew, const u16* slo, const u16* shi,
+                                                  const u16* ca, const u16* cb, bool poison_mode) {
+    if (use_memo) {
+        for (int k = 0; k < memo_visible; ++k) {
+            const double* e = S.memo + 4 * k;
+            if (e[0] == a && e[1] == b) {
+                count_rows(P, S, q_new, cnew, slo, shi);  // the boundary indices are still needed downstream
+                StripResult r;
+                r.mass = e[2];
+                r.cells = (unsigned)e[3];
+                r.poisoned = e[2] != e[2];
+                return r;
+            }
+        }
+    }
+    const StripResult r = strip_pass<COPULA>(P, S, L, parity, true, q_new, cnew, slo, shi, ca, cb, poison_mode);
+    if (use_memo && remember && memo_n < MEMO_SIZE) {
+        if (threadIdx.x == 0) {
+            double* e = S.memo + 4 * memo_n;
+            e[0] = a; e[1] = b; e[2] = r.mass; e[3] = (double)r.cells;
+        }
+        ++memo_n;
+    }
+    return r;
+}
+
 // ---------------------------------------------------------------------------------------------
 // the solve kernel
 // ---------------------------------------------------------------------------------------------
@@ -442,10 +483,14 @@ solve_kernel(KernelParams P, const double* __restrict__ day_params, long long T,
 
     bool have_f3 = false;
     StripResult f3 = {0.0, 0u, false};
+    const bool use_memo = A.n_alpha > 1;
+    int memo_n = 0;
 
     for (int ia = 0; ia < A.n_alpha; ++ia) {
         const double alpha = A.a[ia];
         unsigned long long ncell = 0;
+        if (ia > 0) __syncthreads();  // memo entries of the previous alphas are visible from here on
+        const int memo_visible = memo_n;
         // --- probe 1: F(first)  (calc_var_class.py:114-119)
         if (!have_f3) {
             f3 = strip_pass<COPULA>(P, S, L, parity, true, P.first, S.c[0], nullptr, nullptr, nullptr, S.c[0], poison_mode);
@@ -460,9 +505,11 @@ solve_kernel(KernelParams P, const double* __restrict__ day_params, long long T,
         double prev_upper = (lo2 == P.second_lo) ? P.second_lo : P.first;  // Q6
         StripResult s2;
         if (lo2 == P.first)   // strip (first, second_hi]: new upper boundary, searched above c[0]
-            s2 = strip_pass<COPULA>(P, S, L, parity, true, hi2, S.c[1], S.c[0], nullptr, S.c[0], S.c[1], poison_mode);
+            s2 = strip_memo<COPULA>(P, S, L, parity, use_memo, true, memo_visible, memo_n, lo2, hi2, hi2, S.c[1], S.c[0], nullptr,
+                                    S.c[0], S.c[1], poison_mode);
         else                  // strip (second_lo, first]: new lower boundary, searched below c[0]
-            s2 = strip_pass<COPULA>(P, S, L, parity, true, lo2, S.c[1], nullptr, S.c[0], S.c[1], S.c[0], poison_mode);
+            s2 = strip_memo<COPULA>(P, S, L, parity, use_memo, true, memo_visible, memo_n, lo2, hi2, lo2, S.c[1], nullptr, S.c[0],
+                                    S.c[1], S.c[0], poison_mode);
         ncell += s2.cells;
         double R = (lo2 == P.first) ? f3.mass + s2.mass : f3.mass - s2.mass;
         if ((P.compat & 2u) == 0 && lo2 == P.first) prev_upper = hi2;  // intended behaviour: R = F(hi2)
@@ -488,9 +535,9 @@ solve_kernel(KernelParams P, const double* __restrict__ day_params, long long T,
         if (kase != 4) {
             for (int k = 0; k < P.max_iter; ++k) {
                 const double mid = (lo + hi) / 2;
-                const double a = stack ? lo : mid;
-                const StripResult s = strip_pass<COPULA>(P, S, L, parity, true, mid, cm, cl, ch, stack ? cl : cm,
-                                                         stack ? cm : ch, poison_mode);
+                const double a = stack ? lo : mid, b = stack ? mid : hi;
+                const StripResult s = strip_memo<COPULA>(P, S, L, parity, use_memo, k < MEMO_PER_ALPHA - 1, memo_visible, memo_n, a, b,
+                                                         mid, cm, cl, ch, stack ? cl : cm, stack ? cm : ch, poison_mode);
                 ncell += s.cells;
                 R = (a == prev_upper) ? R + s.mass : R - s.mass;  // adjust_integral (:241-246)
                 if (R == 0.0) zer |= 1u << k;
