@@ -87,3 +87,19 @@ def test_mass_is_monotone_in_the_quantile(backend):
         F = np.array([plan.strip_mass(inp.day_params(), np.column_stack([np.full(4, -100.0), np.full(4, q)])) for q in qs])
     assert np.all(np.diff(F, axis=0) >= 0)
     assert np.all(F[0] < 1e-3) and np.all(F[-1] > 0.9)
+
+
+@pytest.mark.parametrize("name,n,T", [("c2", 1024, 10), ("c4", 512, 12), ("c3", 256, 8)])
+def test_alpha_fusion_equals_separate_solves(backend, name, n, T):
+    """All alphas of a day share the per-axis stage and re-use each other's early strips; every row must equal
+    what a single-alpha launch (the reference's one `calc_var` call per alpha) returns, including the counters."""
+    inp, _ = _inputs(name, n, T)
+    alphas = [0.05, 0.01, 0.025, 0.10, 0.01, 0.001]
+    with backend.VarPlan(inp) as plan:
+        day = inp.day_params()
+        fused = plan.solve(day, alphas, forced_iterations=22)
+        for k, a in enumerate(alphas):
+            alone = plan.solve(day, [a], forced_iterations=22)
+            assert fused.var[k].tobytes() == alone.var[0].tobytes()
+            assert np.array_equal(fused.case[k], alone.case[0])
+            assert np.array_equal(fused.cells[k], alone.cells[0])
