@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "../../include/cvar.h"
+#include "cvar_forecast.cuh"
 #include "cvar_kernels.cuh"
 
 using namespace cvar;
@@ -696,6 +697,175 @@ int cvar_fp64_peak_host(int device, double min_ms, double* tflops_out, double* m
     *tflops_out = flops / (ms * 1e-3) / 1e12;
     if (ms_out) *ms_out = ms;
     return CVAR_OK;
+}
+
+}  // extern "C"
+
+// ---- forecast producers ---------------------------------------------------------------
+namespace {
+
+template <int K>
+void launch_msm(const MsmAsset& A, const double* lik, int64_t T, int N, int64_t stride, const int* level, int q,
+                double* out, int64_t out_stride, double* state_probs, int* status, cudaStream_t st) {
+    const unsigned blocks = (unsigned)((T + MSM_WARPS_PER_CTA - 1) / MSM_WARPS_PER_CTA);
+    msm_filter_kernel<K><<<blocks, 32 * MSM_WARPS_PER_CTA, 0, st>>>(A, lik, (long long)T, N, (long long)stride, level, q, out,
+                                                                    (long long)out_stride, state_probs, status);
+}
+
+int msm_dispatch(int k, const MsmAsset& A, const double* lik, int64_t T, int N, int64_t stride, const int* level, int q,
+                 double* out, int64_t out_stride, double* state_probs, int* status, cudaStream_t st) {
+    switch (k) {
+        case 1: launch_msm<1>(A, lik, T, N, stride, level, q, out, out_stride, state_probs, status, st); break;
+        case 2: launch_msm<2>(A, lik, T, N, stride, level, q, out, out_stride, state_probs, status, st); break;
+        case 3: launch_msm<3>(A, lik, T, N, stride, level, q, out, out_stride, state_probs, status, st); break;
+        case 4: launch_msm<4>(A, lik, T, N, stride, level, q, out, out_stride, state_probs, status, st); break;
+        case 5: launch_msm<5>(A, lik, T, N, stride, level, q, out, out_stride, state_probs, status, st); break;
+        case 6: launch_msm<6>(A, lik, T, N, stride, level, q, out, out_stride, state_probs, status, st); break;
+        case 7: launch_msm<7>(A, lik, T, N, stride, level, q, out, out_stride, state_probs, status, st); break;
+        case 8: launch_msm<8>(A, lik, T, N, stride, level, q, out, out_stride, state_probs, status, st); break;
+        case 9: launch_msm<9>(A, lik, T, N, stride, level, q, out, out_stride, state_probs, status, st); break;
+        case 10: launch_msm<10>(A, lik, T, N, stride, level, q, out, out_stride, state_probs, status, st); break;
+        default: return CVAR_ERR_PARAM;
+    }
+    return (int)cudaGetLastError();
+}
+
+int pick_device(int device) {
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
+        cudaGetLastError();
+        return -1;
+    }
+    if (device < 0 && cudaGetDevice(&device) != cudaSuccess) return -1;
+    return device < ndev ? device : -1;
+}
+
+}  // namespace
+
+extern "C" {
+
+int cvar_msm_forecast_device(int32_t k, int32_t n_assets, const double* stay_prob, const double* vol_states,
+                             const int32_t* level_of_state, int32_t q, const double* returns, int64_t T, int64_t N,
+                             int64_t window_stride, double* probs_by_state, double* state_probs, double* workspace,
+                             int32_t* status, void* stream) {
+    if (!stay_prob || !vol_states || !level_of_state || !returns || !probs_by_state || !workspace || !status) return CVAR_ERR_NULL;
+    if (k < 1 || k > MSM_MAX_K || n_assets < 1 || q < 1 || q > (1 << k)) return CVAR_ERR_PARAM;
+    if (T < 0 || N < 1 || window_stride < 1) return CVAR_ERR_SIZE;
+    if (T == 0) return CVAR_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int S = 1 << k;
+    const int64_t L = (T - 1) * window_stride + N;  // returns per asset
+    for (int a = 0; a < n_assets; ++a) {
+        MsmAsset A;
+        for (int c = 0; c < MSM_MAX_K; ++c) A.stay[c] = c < k ? stay_prob[a * k + c] : 1.0;
+        double* lik = workspace + (size_t)a * L * S;
+        const long long cnt = (long long)L * S;
+        msm_likelihood_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, st>>>(returns + a * L, (long long)L, vol_states + a * S, S, lik);
+        CU_TRY(cudaGetLastError());
+        int rc = msm_dispatch(k, A, lik, T, (int)N, window_stride, level_of_state + a * S, q, probs_by_state + a * q,
+                              (int64_t)n_assets * q, state_probs ? state_probs + (size_t)a * T * S : nullptr, status, st);
+        if (rc) return rc;
+    }
+    return CVAR_OK;
+}
+
+int cvar_msm_forecast_host(int32_t k, int32_t n_assets, const double* stay_prob, const double* vol_states,
+                           const int32_t* level_of_state, int32_t q, const double* returns, int64_t T, int64_t N,
+                           int64_t window_stride, double* probs_by_state, double* state_probs, int32_t* status_out,
+                           double* kernel_ms_out, int device) {
+    if (!stay_prob || !vol_states || !level_of_state || !returns || !probs_by_state) return CVAR_ERR_NULL;
+    if (k < 1 || k > MSM_MAX_K || n_assets < 1 || q < 1 || q > (1 << k)) return CVAR_ERR_PARAM;
+    if (T < 0 || N < 1 || window_stride < 1) return CVAR_ERR_SIZE;
+    device = pick_device(device);
+    if (device < 0) return CVAR_ERR_NO_DEVICE;
+    if (T == 0) return CVAR_OK;
+    DeviceGuard guard(device);
+    const int S = 1 << k;
+    const int64_t L = (T - 1) * window_stride + N;
+    const size_t b_ret = align256(sizeof(double) * n_assets * L), b_vol = align256(sizeof(double) * n_assets * S);
+    const size_t b_lvl = align256(sizeof(int) * n_assets * S), b_stay = 0;
+    const size_t b_out = align256(sizeof(double) * T * n_assets * q);
+    const size_t b_sp = state_probs ? align256(sizeof(double) * n_assets * T * S) : 0;
+    const size_t b_ws = align256(sizeof(double) * n_assets * L * S), b_st = 256;
+    (void)b_stay;
+    char* base = nullptr;
+    CU_TRY(cudaMalloc(&base, b_ret + b_vol + b_lvl + b_out + b_sp + b_ws + b_st));
+    double* d_ret = (double*)base;
+    double* d_vol = (double*)(base + b_ret);
+    int* d_lvl = (int*)(base + b_ret + b_vol);
+    double* d_out = (double*)(base + b_ret + b_vol + b_lvl);
+    double* d_sp = state_probs ? (double*)(base + b_ret + b_vol + b_lvl + b_out) : nullptr;
+    double* d_ws = (double*)(base + b_ret + b_vol + b_lvl + b_out + b_sp);
+    int* d_st = (int*)(base + b_ret + b_vol + b_lvl + b_out + b_sp + b_ws);
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    cudaError_t e = cudaMemcpy(d_ret, returns, sizeof(double) * n_assets * L, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(d_vol, vol_states, sizeof(double) * n_assets * S, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(d_lvl, level_of_state, sizeof(int) * n_assets * S, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemset(d_st, 0, sizeof(int));
+    int rc = (int)e;
+    if (!rc) {
+        cudaEventRecord(e0);
+        rc = cvar_msm_forecast_device(k, n_assets, stay_prob, d_vol, d_lvl, q, d_ret, T, N, window_stride, d_out, d_sp, d_ws,
+                                      d_st, nullptr);
+        cudaEventRecord(e1);
+    }
+    if (!rc) rc = (int)cudaMemcpy(probs_by_state, d_out, sizeof(double) * T * n_assets * q, cudaMemcpyDeviceToHost);
+    if (!rc && state_probs) rc = (int)cudaMemcpy(state_probs, d_sp, sizeof(double) * n_assets * T * S, cudaMemcpyDeviceToHost);
+    int st_host = 0;
+    if (!rc) rc = (int)cudaMemcpy(&st_host, d_st, sizeof(int), cudaMemcpyDeviceToHost);
+    if (status_out) *status_out = st_host;
+    float ms = 0.f;
+    if (!rc && kernel_ms_out && cudaEventElapsedTime(&ms, e0, e1) == cudaSuccess) *kernel_ms_out = ms;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(base);
+    return rc;
+}
+
+int cvar_garch_forecast_host(int32_t n_assets, const double* omega, const int32_t* p, const int32_t* q, const double* alpha,
+                             const double* beta, const double* returns, int64_t T, int64_t N, int64_t window_stride,
+                             double* sigma_out, double* kernel_ms_out, int device) {
+    if (!omega || !p || !q || !alpha || !beta || !returns || !sigma_out) return CVAR_ERR_NULL;
+    if (n_assets < 1 || T < 0 || N < 1 || window_stride < 1) return CVAR_ERR_SIZE;
+    for (int a = 0; a < n_assets; ++a)
+        if (p[a] < 1 || q[a] < 1 || p[a] > GARCH_MAX_ORDER || q[a] > GARCH_MAX_ORDER || p[a] > N || q[a] > N) return CVAR_ERR_PARAM;
+    device = pick_device(device);
+    if (device < 0) return CVAR_ERR_NO_DEVICE;
+    if (T == 0) return CVAR_OK;
+    DeviceGuard guard(device);
+    const int64_t L = (T - 1) * window_stride + N;
+    double *d_ret = nullptr, *d_out = nullptr;
+    CU_TRY(cudaMalloc(&d_ret, sizeof(double) * n_assets * L));
+    cudaError_t e = cudaMalloc(&d_out, sizeof(double) * T * n_assets);
+    if (e != cudaSuccess) { cudaFree(d_ret); return (int)e; }
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    e = cudaMemcpy(d_ret, returns, sizeof(double) * n_assets * L, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        cudaEventRecord(e0);
+        for (int a = 0; a < n_assets; ++a) {
+            GarchAsset G;
+            std::memset(&G, 0, sizeof(G));
+            G.omega = omega[a]; G.p = p[a]; G.q = q[a];
+            for (int i = 0; i < p[a]; ++i) G.alpha[i] = alpha[a * GARCH_MAX_ORDER + i];
+            for (int j = 0; j < q[a]; ++j) G.beta[j] = beta[a * GARCH_MAX_ORDER + j];
+            garch_forecast_kernel<<<(unsigned)((T + 127) / 128), 128>>>(G, d_ret + a * L, (long long)T, (int)N,
+                                                                       (long long)window_stride, d_out + a, (long long)n_assets);
+        }
+        cudaEventRecord(e1);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpy(sigma_out, d_out, sizeof(double) * T * n_assets, cudaMemcpyDeviceToHost);
+    float ms = 0.f;
+    if (e == cudaSuccess && kernel_ms_out && cudaEventElapsedTime(&ms, e0, e1) == cudaSuccess) *kernel_ms_out = ms;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d_ret);
+    cudaFree(d_out);
+    return (int)e;
 }
 
 }  // extern "C"

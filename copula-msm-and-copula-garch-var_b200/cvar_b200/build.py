@@ -15,7 +15,7 @@ PKG_DIR = Path(__file__).resolve().parent
 CSRC = PKG_DIR.parent / "csrc"
 LIB_PATH = PKG_DIR / "libcvar_b200.so"
 SOURCES = ["cvar_api.cu"]
-HEADERS = ["cvar_kernels.cuh", "cvar_math.cuh", "cvar_coeffs.h", "../../include/cvar.h"]
+HEADERS = ["cvar_kernels.cuh", "cvar_math.cuh", "cvar_forecast.cuh", "cvar_coeffs.h", "../../include/cvar.h"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -6,9 +6,47 @@ the solve reads (utils/model_estimation/model/msm_estimation.py:205-248, 283-330
 """
 from __future__ import annotations
 
+import itertools
+
 import numpy as np
 
 from .axis import build_axis
+
+
+# ---- the binomial MSM(k) model itself (markov_switching_multifractal/calc_prob.py:72-108) -------------------------
+def msm_multiplier_table(k: int, m0: float) -> np.ndarray:
+    """(2^k, k) table of multiplier vectors, `itertools.product` order (component 0 varies slowest)."""
+    return np.array(list(itertools.product([m0, 2.0 - m0], repeat=k)))
+
+
+def msm_vol_states(k: int, m0: float, sigma_bar: float) -> np.ndarray:
+    """vol_states[2^k] = sqrt(prod_i M_i) * sigma_bar."""
+    return np.sqrt(np.prod(msm_multiplier_table(k, m0), axis=1)) * sigma_bar
+
+
+def msm_switch_probs(k: int, b: float, gamma: float) -> np.ndarray:
+    """gamma_i, i = 0..k-1: probability that component i is redrawn in one step."""
+    return 1.0 - (1.0 - gamma) ** (b ** np.arange(k))
+
+
+def msm_stay_probs(k: int, b: float, gamma: float) -> np.ndarray:
+    """p_i = 1 - gamma_i / 2: probability that component i keeps its value over one step."""
+    return 1.0 - msm_switch_probs(k, b, gamma) / 2.0
+
+
+def msm_transition_matrix(k: int, m0: float, b: float, gamma: float) -> np.ndarray:
+    """Dense P[i, j] = prod_c (p_c if equal else 1 - p_c); the Kronecker product of k 2x2 factors."""
+    table = msm_multiplier_table(k, m0)
+    p = msm_stay_probs(k, b, gamma)
+    same = table[:, None, :] == table[None, :, :]
+    return np.prod(np.where(same, p, 1.0 - p), axis=2)
+
+
+def state_levels(vol_states, tol: float = 1e-6):
+    """(level_of_state[S], sigma_levels[q]) with the reference's rounding (msm_estimation.py:228-229)."""
+    rounded = np.round(np.asarray(vol_states, float) / tol) * tol
+    uniq, inv = np.unique(rounded, return_inverse=True)
+    return inv.astype(np.int32), uniq
 
 
 def merge_states(vol_states, probs, tol: float = 1e-6):

@@ -18,12 +18,11 @@ markov_switching_multifractal/calc_prob.py:72-108 (state enumeration in
 """
 from __future__ import annotations
 
-import itertools
-
 import numpy as np
 
 from .inputs import HotPathInputs, make_inputs
-from .msm_layout import merge_states  # noqa: F401  (re-exported)
+from .msm_layout import (merge_states, msm_multiplier_table, msm_switch_probs, msm_transition_matrix,  # noqa: F401
+                         msm_vol_states)
 
 # asset-level constants of SURVEY §8(d)
 GARCH_ASSETS = ((0.02, 0.09, 0.89, 1), (0.03, 0.08, 0.90, 2))       # omega, alpha, beta, seed
@@ -61,29 +60,6 @@ def kalman_sigma_path(T: int, assets=KALMAN_ASSETS) -> np.ndarray:
 # ----------------------------------------------------------------------------
 # binomial MSM(k)
 # ----------------------------------------------------------------------------
-def msm_multiplier_table(k: int, m0: float) -> np.ndarray:
-    """(2^k, k) table of multiplier vectors, `itertools.product` order."""
-    return np.array(list(itertools.product([m0, 2.0 - m0], repeat=k)))
-
-
-def msm_vol_states(k: int, m0: float, sigma_bar: float) -> np.ndarray:
-    """vol_states[2^k] = sigma_bar * sqrt(prod_i M_i)."""
-    return np.sqrt(np.prod(msm_multiplier_table(k, m0), axis=1)) * sigma_bar
-
-
-def msm_switch_probs(k: int, b: float, gamma: float) -> np.ndarray:
-    """gamma_i, i = 0..k-1: probability that component i is redrawn in one step."""
-    return 1.0 - (1.0 - gamma) ** (b ** np.arange(k))
-
-
-def msm_transition_matrix(k: int, m0: float, b: float, gamma: float) -> np.ndarray:
-    """P[i, j]: product over components of (1-gamma_c/2) if equal else gamma_c/2."""
-    table = msm_multiplier_table(k, m0)
-    g = msm_switch_probs(k, b, gamma)
-    same = table[:, None, :] == table[None, :, :]
-    return np.prod(np.where(same, 1.0 - g / 2.0, g / 2.0), axis=2)
-
-
 def msm_simulate_returns(T: int, k: int, m0: float, sigma_bar: float, b: float, gamma: float, seed: int):
     """One simulated MSM return path of length T (percent units)."""
     rng = np.random.default_rng(seed)

@@ -224,6 +224,47 @@ int cvar_copula_density_host(int32_t copula, double rho, double nu, double theta
  */
 int cvar_fp64_peak_host(int device, double min_ms, double* tflops_out, double* ms_out);
 
+/* =====================================================================================================
+ * Forecast producers: what fills `day_params` from rolling windows of centred returns.
+ * Rolling window w of an asset is returns[w * window_stride .. w * window_stride + N) -- window_stride = 1 for the
+ * reference's overlapping windows (data_loader/load_data.py:131-137), N for independent windows.
+ * ===================================================================================================== */
+
+/*
+ * Binomial MSM(k): filtered state distribution at the end of every window, merged to the q distinct vol levels.
+ * Replaces MSMEstimation.forecasts_array + sum_forecast_by_state (utils/model_estimation/model/msm_estimation.py:143-248),
+ * i.e. calc_forecasts -> ProbEstimation.calc_state_prob (markov_switching_multifractal/calc_marginals.py:33-38,
+ * calc_prob.py:8-69, 110-122).
+ *   stay_prob      [n_assets][k]   p_c = 1 - gamma_c/2, gamma_c = 1-(1-gamma)^(b^c)   (calc_prob.py:90-101)   HOST
+ *   vol_states     [n_assets][2^k] sigma_s in itertools.product order (calc_prob.py:103-108)
+ *   level_of_state [n_assets][2^k] index of each state's merged vol level, 0..q-1
+ *   returns        [n_assets][(T-1)*window_stride + N]
+ *   probs_by_state [T][n_assets][q]   == the solve's day_params for CVAR_MARGINAL_MIXTURE with n_assets = 2
+ *   state_probs    [n_assets][T][2^k] un-merged filtered probabilities, may be NULL
+ *   status         set to 1 if a window's normalising constant was 0 (the reference then marks the run failed);
+ *                  that window's probabilities are NaN
+ * _device: vol_states, level_of_state, returns, outputs, status and workspace ([n_assets][L][2^k] doubles,
+ *          L = (T-1)*window_stride + N) are DEVICE pointers; stay_prob is a host pointer; enqueues on `stream`.
+ */
+int cvar_msm_forecast_host(int32_t k, int32_t n_assets, const double* stay_prob, const double* vol_states,
+                           const int32_t* level_of_state, int32_t q, const double* returns, int64_t T, int64_t N,
+                           int64_t window_stride, double* probs_by_state, double* state_probs, int32_t* status_out,
+                           double* kernel_ms_out, int device);
+int cvar_msm_forecast_device(int32_t k, int32_t n_assets, const double* stay_prob, const double* vol_states,
+                             const int32_t* level_of_state, int32_t q, const double* returns, int64_t T, int64_t N,
+                             int64_t window_stride, double* probs_by_state, double* state_probs, double* workspace,
+                             int32_t* status, void* stream);
+
+/*
+ * GARCH(p,q) one-step volatility forecast per window: replaces GarchEstimation.compute_forecast ->
+ * calc_forecast (utils/model_estimation/model/garch_estimation.py:190-231, garch/forecast.py:5-18,
+ * garch/estimation.py:40-65).  alpha / beta are [n_assets][8] (unused entries ignored), p, q <= 8.
+ *   sigma_out [T][n_assets] == the solve's day_params for CVAR_MARGINAL_SINGLE with n_assets = 2
+ */
+int cvar_garch_forecast_host(int32_t n_assets, const double* omega, const int32_t* p, const int32_t* q, const double* alpha,
+                             const double* beta, const double* returns, int64_t T, int64_t N, int64_t window_stride,
+                             double* sigma_out, double* kernel_ms_out, int device);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,98 @@
+"""GPU forecast producers against the reference's golden vectors and the oracle."""
+import numpy as np
+import pytest
+
+from conftest import GOLDEN_DIR
+
+pytestmark = pytest.mark.gpu
+
+G = dict(np.load(GOLDEN_DIR / "forecast_producers.npz"))
+MSM = sorted({k.split("__")[0] for k in G if k.startswith("msm")})
+GARCH = sorted({k.split("__")[0] for k in G if k.startswith("garch")})
+
+
+def case(name):
+    return {k.split("__")[1]: v for k, v in G.items() if k.startswith(name + "__")}
+
+
+@pytest.fixture(scope="module")
+def fc(cuda_device):
+    from cvar_b200 import forecast
+    return forecast
+
+
+@pytest.mark.parametrize("name", MSM)
+def test_msm_state_filter_matches_reference(fc, name):
+    """Kronecker-factored butterflies sum in a different order than the reference's dense rows: 1e-12 relative."""
+    c = case(name)
+    prm = fc.MsmParams(float(c["m0"]), float(c["sigma_bar"]), float(c["b"]), float(c["gamma"]))
+    pbs, sig, sp, info = fc.msm_forecast(c["series"][None, :], [prm], int(c["k"]), int(c["N"]), return_state_probs=True)
+    assert not info["degenerate"] and sp.shape == (1,) + c["ref"].shape
+    np.testing.assert_allclose(sp[0], c["ref"], rtol=1e-12, atol=1e-300)
+    # merged levels == the reference's sum_forecast_by_state on the reference's own probabilities
+    from cvar_b200.msm_layout import merge_states, msm_vol_states
+    vols = msm_vol_states(int(c["k"]), prm.m0, prm.sigma_bar)[None, :]
+    want_pbs, want_sig = merge_states(vols, c["ref"][None, :, :])
+    assert np.array_equal(sig, want_sig)
+    np.testing.assert_allclose(pbs, want_pbs, rtol=1e-12, atol=1e-300)
+
+
+@pytest.mark.parametrize("name", GARCH)
+def test_garch_forecast_matches_reference(fc, name):
+    c = case(name)
+    sigma, _ = fc.garch_forecast(c["series"][None, :], [float(c["omega"])], [c["alpha"]], [c["beta"]], int(c["N"]))
+    np.testing.assert_allclose(sigma[:, 0], c["ref"], rtol=4e-16, atol=0)
+
+
+def test_independent_windows_mode_equals_rolling_mode(fc):
+    c = case("msm_k4")
+    prm = [fc.MsmParams(float(c["m0"]), float(c["sigma_bar"]), float(c["b"]), float(c["gamma"]))]
+    N, T = int(c["N"]), int(c["T"])
+    rolling, _, _ = fc.msm_forecast(c["series"][None, :], prm, 4, N)
+    windows = np.array([c["series"][t:t + N] for t in range(T)])
+    assert np.array_equal(fc.rolling_series(windows), c["series"])
+    separate, _, _ = fc.msm_forecast(windows.reshape(1, -1), prm, 4, N, window_stride=N)
+    assert np.array_equal(rolling, separate)
+
+
+def test_returns_to_var_pipeline_matches_the_oracle_pipeline(fc):
+    """Two assets, MSM(k=4): GPU filter -> GPU solve  vs  oracle filter -> reference merge -> oracle solve."""
+    from cvar_b200 import synthetic as syn
+    from cvar_b200.backend import VarPlan
+    from cvar_b200.inputs import make_inputs
+    from cvar_b200.msm_layout import merge_states
+    from oracle import forecast_oracle as fo, var_oracle as vo
+    k, N, T = 4, 80, 6
+    prm = [fc.MsmParams(0.4, 1.1, 3.0, 0.3), fc.MsmParams(0.55, 1.4, 5.0, 0.2)]
+    series = np.array([syn.msm_simulate_returns(T + N - 1, k, p.m0, p.sigma_bar, p.b, p.gamma, 40 + i) for i, p in enumerate(prm)])
+    pbs, sig, _ = fc.msm_forecast(series, prm, k, N)
+    inp = make_inputs("student", "mixture", 96, rho=0.6, nu=5.3, probs=pbs, sigma_states=sig)
+    with VarPlan(inp) as plan:
+        gpu = plan.solve(inp.day_params(), [0.01, 0.05])
+    sp = np.array([fo.msm_forecast(series[a], k, prm[a].m0, prm[a].sigma_bar, prm[a].b, prm[a].gamma, N, T) for a in range(2)])
+    vols = np.array([fo.msm_tables(k, p.m0, p.sigma_bar, p.b, p.gamma)[0] for p in prm])
+    o_pbs, o_sig = merge_states(vols, sp)
+    o_inp = make_inputs("student", "mixture", 96, rho=0.6, nu=5.3, probs=o_pbs, sigma_states=o_sig)
+    for j, a in enumerate((0.01, 0.05)):
+        assert np.max(np.abs(gpu.var[j] - vo.calc_var(o_inp, a).var)) <= 1e-7
+
+
+def test_mirror_adapters_run_their_forecast_stage_on_the_gpu(fc):
+    """MSMEstimation.forecasts_array / GarchEstimation.compute_forecast with the reference's argument layout."""
+    from utils.model_estimation.model.garch_estimation import GarchEstimation
+    from utils.model_estimation.model.msm_estimation import MSMEstimation
+    c = case("msm_k3")
+    N, T = int(c["N"]), int(c["T"])
+    windows = {f"d{t}": {"A": c["series"][t:t + N], "B": c["series"][t:t + N] * 1.0} for t in range(T)}
+    params = {tk: {"optimal_params": {"m_0": float(c["m0"]), "sig": float(c["sigma_bar"]), "b": float(c["b"]), "gamma": float(c["gamma"])}}
+              for tk in ("A", "B")}
+    fa = MSMEstimation().forecasts_array(windows, params, 3)
+    assert fa.shape == (2, T, 8)
+    np.testing.assert_allclose(fa[0], c["ref"], rtol=1e-12)
+    np.testing.assert_allclose(fa[1], c["ref"], rtol=1e-12)
+    g = case("garch_21")
+    N, T = int(g["N"]), int(g["T"])
+    windows = {f"d{t}": {"A": g["series"][t:t + N]} for t in range(T)}
+    params = {"A": {"optimal_params": {"best_pq": (2, 1), "best_params": [float(g["omega"]), *g["alpha"], *g["beta"]], "best_bic": 0.0}}}
+    (sigma,) = GarchEstimation().compute_forecast(windows, params)
+    np.testing.assert_allclose(sigma[:, 0], g["ref"], rtol=4e-16)
