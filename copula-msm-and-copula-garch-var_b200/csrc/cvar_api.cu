@@ -824,6 +824,51 @@ int cvar_msm_forecast_host(int32_t k, int32_t n_assets, const double* stay_prob,
     return rc;
 }
 
+int cvar_kalman_forecast_host(int32_t n_assets, const double* a, const double* l, const double* q, double ukf_alpha,
+                              double ukf_beta, double ukf_kappa, const double* returns, int64_t T, int64_t N,
+                              int64_t window_stride, double* sigma_out, int32_t* status_out, double* kernel_ms_out, int device) {
+    if (!a || !l || !q || !returns || !sigma_out) return CVAR_ERR_NULL;
+    if (n_assets < 1 || T < 0 || N < 1 || window_stride < 1) return CVAR_ERR_SIZE;
+    device = pick_device(device);
+    if (device < 0) return CVAR_ERR_NO_DEVICE;
+    if (T == 0) return CVAR_OK;
+    DeviceGuard guard(device);
+    const int64_t L = (T - 1) * window_stride + N;
+    double *d_ret = nullptr, *d_out = nullptr;
+    int* d_st = nullptr;
+    CU_TRY(cudaMalloc(&d_ret, sizeof(double) * n_assets * L));
+    cudaError_t e = cudaMalloc(&d_out, sizeof(double) * T * n_assets);
+    if (e == cudaSuccess) e = cudaMalloc(&d_st, sizeof(int));
+    if (e != cudaSuccess) { cudaFree(d_ret); cudaFree(d_out); return (int)e; }
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    e = cudaMemcpy(d_ret, returns, sizeof(double) * n_assets * L, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemset(d_st, 0, sizeof(int));
+    if (e == cudaSuccess) {
+        cudaEventRecord(e0);
+        for (int k = 0; k < n_assets; ++k) {
+            KalmanAsset K{a[k], l[k], q[k], ukf_alpha, ukf_beta, ukf_kappa};
+            kalman_forecast_kernel<<<(unsigned)((T + 127) / 128), 128>>>(K, d_ret + k * L, (long long)T, (int)N,
+                                                                        (long long)window_stride, d_out + k, (long long)n_assets, d_st);
+        }
+        cudaEventRecord(e1);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpy(sigma_out, d_out, sizeof(double) * T * n_assets, cudaMemcpyDeviceToHost);
+    int st = 0;
+    if (e == cudaSuccess) e = cudaMemcpy(&st, d_st, sizeof(int), cudaMemcpyDeviceToHost);
+    if (status_out) *status_out = st;
+    float ms = 0.f;
+    if (e == cudaSuccess && kernel_ms_out && cudaEventElapsedTime(&ms, e0, e1) == cudaSuccess) *kernel_ms_out = ms;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d_ret);
+    cudaFree(d_out);
+    cudaFree(d_st);
+    return (int)e;
+}
+
 int cvar_garch_forecast_host(int32_t n_assets, const double* omega, const int32_t* p, const int32_t* q, const double* alpha,
                              const double* beta, const double* returns, int64_t T, int64_t N, int64_t window_stride,
                              double* sigma_out, double* kernel_ms_out, int device) {

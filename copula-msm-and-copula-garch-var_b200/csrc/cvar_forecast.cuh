@@ -160,4 +160,68 @@ __global__ void garch_forecast_kernel(GarchAsset G, const double* __restrict__ r
     sigma_out[w * out_stride] = sqrt(G.omega + fa + fb);
 }
 
+// Kalman mean-reverting log-vol model: scalar unscented filter, forecast = exp(last PREDICTED state mean)
+// (kalman_mean_reverting/estimate.py:231-281 `calculate_loglikelihood`, forecast.py:5-12).  One thread per
+// (window, asset).  The reference's peculiarities are kept: sigma-point weights built with L = 2 also for the
+// one-dimensional update (three points, weights that do not sum to one), measurement h = phi(eta)|eta|,
+// eta = r / exp(x), covariance regularisation 1e-8 when the variance is not positive.
+struct KalmanAsset {
+    double a, l, q;          // mean reversion speed, long-run mean, vol of the log-vol process
+    double alpha, beta, kappa;  // UKF tuning (defaults 1.6, 2, 1.75)
+};
+
+__global__ void kalman_forecast_kernel(KalmanAsset K, const double* __restrict__ returns, long long T, int N,
+                                       long long window_stride, double* __restrict__ sigma_out, long long out_stride,
+                                       int* __restrict__ status) {
+    const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= T) return;
+    const double* r = returns + w * window_stride;
+    const double L = 2.0;
+    const double lambda = K.alpha * K.alpha * (L + K.kappa) - L;
+    const double phi = sqrt(L + lambda);
+    const double w_rest = 1.0 / (2.0 * (L + lambda));
+    const double wm0 = lambda / (L + lambda);
+    const double wc0 = wm0 + (1.0 - K.alpha * K.alpha + K.beta);
+    double mean = K.l, var = K.q;  // init_log_vol = l, init_var = q (forecast.py:9)
+    double x_pred = 0.0;
+    bool failed = false;
+    for (int t = 0; t < N; ++t) {
+        // prediction: sigma points of the augmented state (x, noise) with covariance diag(var, 1)
+        double dv = var;
+        if (dv <= 0.0) dv += 1e-8;
+        const double sv = sqrt(dv);
+        const double base = K.a * (mean - K.l) + K.l;
+        const double X0 = base, X1 = K.a * (mean + phi * sv - K.l) + K.l, X2 = base + K.q * phi;
+        const double X3 = K.a * (mean - phi * sv - K.l) + K.l, X4 = base + K.q * (-phi);
+        x_pred = X0 * wm0 + X1 * w_rest + X2 * w_rest + X3 * w_rest + X4 * w_rest;
+        const double d0 = X0 - x_pred, d1 = X1 - x_pred, d2 = X2 - x_pred, d3 = X3 - x_pred, d4 = X4 - x_pred;
+        const double P = d0 * wc0 * d0 + d1 * w_rest * d1 + d2 * w_rest * d2 + d3 * w_rest * d3 + d4 * w_rest * d4;
+        // update with return t on three sigma points
+        const double sp = sqrt(P);
+        const double Y[3] = {x_pred, x_pred + phi * sp, x_pred - phi * sp};
+        const double wm2[3] = {wm0, w_rest, w_rest};
+        double h[3], Z = 0.0;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const double eta = r[t] / exp(Y[k]);
+            h[k] = (0.3989422804014327 * exp(-0.5 * eta * eta)) * fabs(eta);
+            Z += wm2[k] * h[k];
+        }
+        if (!(Z > 0.0) || Z < 1e-10) {
+            failed = true;
+            break;
+        }
+        double m = 0.0;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) m += (wm2[k] * Y[k] * h[k]) / Z;
+        double v = 0.0;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) v += wm2[k] * ((h[k] / Z) * ((Y[k] - m) * (Y[k] - m)));
+        mean = m;
+        var = v;
+    }
+    if (failed) atomicExch(status, 1);
+    sigma_out[w * out_stride] = failed ? NAN : exp(x_pred);
+}
+
 }  // namespace cvar

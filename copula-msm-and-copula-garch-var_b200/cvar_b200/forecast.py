@@ -95,3 +95,19 @@ def garch_forecast(returns, omega, alpha_vects, beta_vects, N: int, *, window_st
                                               _ptr(out), C.byref(ms), device)
     _lib.check(st, "cvar_garch_forecast_host")
     return out, {"kernel_ms": ms.value, "T": T}
+
+
+def kalman_forecast(returns, a, l, q, N: int, *, window_stride: int = 1, ukf=(1.6, 2.0, 1.75), device: int = -1):
+    """Kalman mean-reverting log-vol forecast exp(last predicted state mean) per rolling window: sigma (T, n_assets)."""
+    r = np.ascontiguousarray(np.atleast_2d(returns), dtype=np.float64)
+    na, L = r.shape
+    if (L - N) % window_stride or L < N:
+        raise ValueError("series length does not match (T-1)*window_stride + N")
+    T = (L - N) // window_stride + 1
+    av, lv, qv = (np.ascontiguousarray(np.broadcast_to(np.asarray(v, dtype=np.float64), (na,))) for v in (a, l, q))
+    out = np.empty((T, na))
+    status, ms = C.c_int32(0), C.c_double(0.0)
+    st = _lib.load().cvar_kalman_forecast_host(na, _ptr(av), _ptr(lv), _ptr(qv), float(ukf[0]), float(ukf[1]), float(ukf[2]),
+                                               _ptr(r), T, N, window_stride, _ptr(out), C.byref(status), C.byref(ms), device)
+    _lib.check(st, "cvar_kalman_forecast_host")
+    return out, {"kernel_ms": ms.value, "T": T, "failed": bool(status.value)}

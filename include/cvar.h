@@ -265,6 +265,19 @@ int cvar_garch_forecast_host(int32_t n_assets, const double* omega, const int32_
                              const double* beta, const double* returns, int64_t T, int64_t N, int64_t window_stride,
                              double* sigma_out, double* kernel_ms_out, int device);
 
+/*
+ * Kalman mean-reverting log-volatility model: exp(last predicted state mean) of the scalar unscented filter per
+ * window.  Replaces MeanRevertingEstimation.compute_forecast -> calc_forecast
+ * (utils/model_estimation/model/mean_reverting_estimation.py:192-232, kalman_mean_reverting/forecast.py:5-12,
+ * kalman_mean_reverting/estimate.py:231-281).  a, l, q are [n_assets]; ukf_alpha/beta/kappa default to 1.6, 2, 1.75
+ * in the reference.  status 1 = the filter's normalising constant collapsed in some window (the reference returns
+ * an error tuple there); that window's forecast is NaN.
+ *   sigma_out [T][n_assets]
+ */
+int cvar_kalman_forecast_host(int32_t n_assets, const double* a, const double* l, const double* q, double ukf_alpha,
+                              double ukf_beta, double ukf_kappa, const double* returns, int64_t T, int64_t N,
+                              int64_t window_stride, double* sigma_out, int32_t* status_out, double* kernel_ms_out, int device);
+
 #ifdef __cplusplus
 }
 #endif

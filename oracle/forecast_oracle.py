@@ -66,3 +66,41 @@ def garch_forecast_one(omega, alpha_vect, beta_vect, returns):
 
 def garch_forecast(series, omega, alpha_vect, beta_vect, N, T):
     return np.array([garch_forecast_one(omega, alpha_vect, beta_vect, np.asarray(series[t:t + N], float)) for t in range(T)])
+
+
+def kalman_forecast_one(returns, a, l, q, alpha=1.6, beta=2.0, kappa=1.75):
+    """exp(last predicted state mean) of the scalar unscented filter (kalman_mean_reverting/estimate.py:231-281 with
+    init_log_vol = l, init_var = q as forecast.py:9 passes them).  Returns NaN where the reference returns its error tuple."""
+    L = 2
+    lam = (alpha ** 2) * (L + kappa) - L
+    wm = np.full(2 * L + 1, 1 / (2 * (L + lam)))
+    wc = wm.copy()
+    wm[0] = lam / (L + lam)
+    wc[0] = wm[0] + (1 - alpha ** 2 + beta)
+    wm2 = np.full(L + 1, 1 / (2 * (L + lam)))
+    wm2[0] = lam / (L + lam)
+    phi = np.sqrt(L + lam)
+    mean, var, x_mean = l, q, 0.0
+    for t in range(len(returns)):
+        d = var if var > 0 else var + 1e-8                      # custom_cholesky of diag(var, 1)
+        sv = np.sqrt(d)
+        x1 = np.array([mean, mean + phi * sv, mean, mean - phi * sv, mean])
+        x2 = np.array([0.0, 0.0, phi, 0.0, -phi])
+        X = a * (x1 - l) + l + q * x2
+        x_mean = np.dot(X, wm)
+        diff = X - x_mean
+        P = np.dot(diff * wc, diff)
+        sp = np.sqrt(P)
+        Y = np.array([x_mean, x_mean + phi * sp, x_mean - phi * sp])
+        eta = returns[t] / np.exp(Y)
+        h = (1 / np.sqrt(2 * np.pi)) * np.exp(-0.5 * eta ** 2) * np.abs(eta)
+        Z = np.sum(wm2 * h)
+        if Z <= 0 or Z < 1e-10:
+            return np.nan
+        mean = np.sum((wm2 * Y * h) / Z)
+        var = np.sum(wm2 * ((h / Z) * (Y - mean) ** 2))
+    return np.exp(x_mean)
+
+
+def kalman_forecast(series, a, l, q, N, T):
+    return np.array([kalman_forecast_one(np.asarray(series[t:t + N], float), a, l, q) for t in range(T)])

@@ -6,6 +6,7 @@ import sys
 import numpy as np
 
 from garch.forecast import calc_forecast as garch_calc_forecast                          # reference
+from kalman_mean_reverting.forecast import calc_forecast as kalman_calc_forecast         # reference
 from markov_switching_multifractal.calc_marginals import calc_forecasts as msm_calc_forecasts   # reference
 
 
@@ -18,6 +19,8 @@ def main(path_in, path_out):
         if c["kind"] == "msm":
             res = np.array([msm_calc_forecasts(c["k"], c["m0"], c["sigma_bar"], c["b"], c["gamma"], series[t:t + N])
                             for t in range(T)])
+        elif c["kind"] == "kalman":
+            res = np.array([kalman_calc_forecast(series[t:t + N], c["a"], c["l"], c["q"]) for t in range(T)])
         else:
             res = np.array([garch_calc_forecast(c["omega"], np.asarray(c["alpha"], float), np.asarray(c["beta"], float),
                                                 series[t:t + N]) for t in range(T)])

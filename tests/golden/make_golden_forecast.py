@@ -33,6 +33,15 @@ def build_cases():
     ]:
         series = rng.standard_normal(T + N - 1) * 1.1
         cases.append(dict(kind="garch", name=name, omega=omega, alpha=alpha, beta=beta, N=N, T=T, series=series))
+    for name, a, l, q, N, T, seed in [("kalman_a", 0.97, 0.0, 0.15, 200, 6, 41), ("kalman_b", 0.9, 0.3, 0.3, 150, 5, 42),
+                                       ("kalman_c", 0.99, -0.4, 0.05, 300, 4, 43)]:
+        rng = np.random.default_rng(seed)
+        x, logvol = l, []
+        for _ in range(T + N - 1):
+            x = a * (x - l) + l + q * rng.standard_normal()
+            logvol.append(x)
+        series = np.exp(np.array(logvol)) * rng.standard_normal(T + N - 1)
+        cases.append(dict(kind="kalman", name=name, a=a, l=l, q=q, N=N, T=T, series=series))
     return cases
 
 

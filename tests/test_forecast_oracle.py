@@ -8,6 +8,7 @@ from oracle import forecast_oracle as fo
 G = dict(np.load(GOLDEN_DIR / "forecast_producers.npz"))
 MSM = sorted({k.split("__")[0] for k in G if k.startswith("msm")})
 GARCH = sorted({k.split("__")[0] for k in G if k.startswith("garch")})
+KALMAN = sorted({k.split("__")[0] for k in G if k.startswith("kalman")})
 
 
 def case(name):
@@ -29,6 +30,13 @@ def test_garch_forecast_oracle_matches_reference(name):
     c = case(name)
     got = fo.garch_forecast(c["series"], float(c["omega"]), c["alpha"], c["beta"], int(c["N"]), int(c["T"]))
     assert got.tobytes() == c["ref"].tobytes()
+
+
+@pytest.mark.parametrize("name", KALMAN)
+def test_kalman_forecast_oracle_matches_reference(name):
+    c = case(name)
+    got = fo.kalman_forecast(c["series"], float(c["a"]), float(c["l"]), float(c["q"]), int(c["N"]), int(c["T"]))
+    np.testing.assert_allclose(got, c["ref"], rtol=1e-13)
 
 
 def test_kronecker_structure_of_the_transition_matrix():

@@ -9,6 +9,7 @@ pytestmark = pytest.mark.gpu
 G = dict(np.load(GOLDEN_DIR / "forecast_producers.npz"))
 MSM = sorted({k.split("__")[0] for k in G if k.startswith("msm")})
 GARCH = sorted({k.split("__")[0] for k in G if k.startswith("garch")})
+KALMAN = sorted({k.split("__")[0] for k in G if k.startswith("kalman")})
 
 
 def case(name):
@@ -42,6 +43,24 @@ def test_garch_forecast_matches_reference(fc, name):
     c = case(name)
     sigma, _ = fc.garch_forecast(c["series"][None, :], [float(c["omega"])], [c["alpha"]], [c["beta"]], int(c["N"]))
     np.testing.assert_allclose(sigma[:, 0], c["ref"], rtol=4e-16, atol=0)
+
+
+@pytest.mark.parametrize("name", KALMAN)
+def test_kalman_forecast_matches_reference(fc, name):
+    c = case(name)
+    sigma, info = fc.kalman_forecast(c["series"][None, :], [float(c["a"])], [float(c["l"])], [float(c["q"])], int(c["N"]))
+    assert not info["failed"]
+    np.testing.assert_allclose(sigma[:, 0], c["ref"], rtol=1e-12)
+
+
+def test_kalman_adapter_runs_on_the_gpu(fc):
+    from utils.model_estimation.model.mean_reverting_estimation import MeanRevertingEstimation
+    c = case("kalman_b")
+    N, T = int(c["N"]), int(c["T"])
+    windows = {f"d{t}": {"A": c["series"][t:t + N]} for t in range(T)}
+    params = {"A": {"optimal_params": {"a": float(c["a"]), "l": float(c["l"]), "q": float(c["q"])}}}
+    (sigma,) = MeanRevertingEstimation().compute_forecast(windows, params)
+    np.testing.assert_allclose(sigma[:, 0], c["ref"], rtol=1e-12)
 
 
 def test_independent_windows_mode_equals_rolling_mode(fc):
