@@ -115,6 +115,45 @@ class ValueAtRiskCalcualtion:
         self._bind_hooks()
         return self
 
+    @classmethod
+    def from_returns(cls, VaRCalculationMethod, returns, in_sample_data_num, in_sample_params, copula_params, *,
+                     num_points=100, weights=np.array([0.5, 0.5]), k=None):
+        """Returns -> forecasts -> ready-to-solve driver, with the forecast stage on the GPU.
+
+        returns            : DataFrame (columns = tickers) or array (days, 2) of percent log-returns
+        in_sample_data_num : N, length of the in-sample period and of every rolling window
+        in_sample_params   : fitted model parameters in the reference's own layout, one entry per ticker/column
+                             ({name: {'optimal_params': {...}}}: GARCH best_pq/best_params, MSM m_0/sig/b/gamma,
+                             Kalman a/l/q) -- fitting itself is outside this backend
+        copula_params      : as `copula_integrations_params` returns them
+
+        Follows the reference's data preparation (data_loader/load_data.py:105-137): centring by the in-sample mean,
+        rolling window i = centred returns[i : i+N], `ptf_mean = sum(mean_returns * weights)`,
+        `out_sample_data = returns[N:]`.
+        """
+        N = int(in_sample_data_num)
+        values = returns.to_numpy(dtype=float) if hasattr(returns, "to_numpy") else np.asarray(returns, dtype=float)
+        if values.ndim != 2 or values.shape[1] != 2:
+            raise NotImplementedError("the B200 backend covers two-asset portfolios")
+        if values.shape[0] <= N:
+            raise ValueError(f"Not enough returns for in-sample estimation. Required: {N + 1}, Available: {values.shape[0]}")
+        weights = np.asarray(weights, float)
+        mean_returns = values[:N].mean(axis=0)
+        T = values.shape[0] - N
+        series = np.ascontiguousarray((values - mean_returns)[: T + N - 1].T)
+        m = VaRCalculationMethod
+        kw = dict(num_points=num_points, weights=weights, ptf_mean=float(np.sum(mean_returns * weights)),
+                  out_sample_data=returns.iloc[N:] if hasattr(returns, "iloc") else values[N:])
+        if m.marginal_family == "single":
+            (sigma,) = m.estimation_method.forecast_from_series(series, in_sample_params, N)
+            self = cls.from_forecasts(m, copula_params, sigma=sigma, **kw)
+        else:
+            pbs, sig = m.estimation_method.forecast_from_series(series, in_sample_params, N, k=k)
+            self = cls.from_forecasts(m, copula_params, probs_by_state=pbs, sigma_states=sig, **kw)
+        self.in_sample_data_num, self.in_sample_params = N, in_sample_params
+        self.mean_returns = dict(zip(getattr(returns, "columns", range(2)), mean_returns))
+        return self
+
     def _bind_hooks(self):
         m = self.VaRCalculationMethod
         self.copula_function = m.copula_density

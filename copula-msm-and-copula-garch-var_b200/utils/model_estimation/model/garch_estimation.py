@@ -18,19 +18,25 @@ class GarchEstimation(SingleNormalEstimation):
         if not rolling_windows_dict or not in_sample_params:
             raise OutOfScopeStage("GARCH forecasts need rolling windows and fitted parameters (fitting itself is outside "
                                   "the GPU hot path); or pass sigma_forecasts= to the adapter")
-        from cvar_b200.forecast import garch_forecast, rolling_series
+        from cvar_b200.forecast import rolling_series
         tickers = list(in_sample_params)
         windows = [np.array([w[t] for w in rolling_windows_dict.values()], dtype=float) for t in tickers]
         N = windows[0].shape[1]
+        series = [rolling_series(w) for w in windows]
+        if all(s is not None for s in series):
+            return self.forecast_from_series(np.array(series), in_sample_params, N)
+        return self.forecast_from_series(np.array([w.reshape(-1) for w in windows]), in_sample_params, N, window_stride=N)
+
+    @staticmethod
+    def forecast_from_series(series, in_sample_params, N, window_stride=1, **_):
+        """[sigma[T, dim]] from centred return series (dim, (T-1)*window_stride + N); one row of `series` per ticker of
+        `in_sample_params` (in its order)."""
+        from cvar_b200.forecast import garch_forecast
         omega, alphas, betas = [], [], []
-        for t in tickers:
+        for t in in_sample_params:
             prm = in_sample_params[t]["optimal_params"]
             p = prm["best_pq"][0]
             best = np.asarray(prm["best_params"], dtype=float)
             omega.append(best[0]); alphas.append(best[1:p + 1]); betas.append(best[p + 1:])
-        series = [rolling_series(w) for w in windows]
-        if all(s is not None for s in series):
-            sigma, _ = garch_forecast(np.array(series), omega, alphas, betas, N)
-        else:
-            sigma, _ = garch_forecast(np.array([w.reshape(-1) for w in windows]), omega, alphas, betas, N, window_stride=N)
+        sigma, _ = garch_forecast(series, omega, alphas, betas, N, window_stride=window_stride)
         return [sigma]

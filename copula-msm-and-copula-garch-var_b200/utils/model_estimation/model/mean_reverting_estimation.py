@@ -18,16 +18,21 @@ class MeanRevertingEstimation(SingleNormalEstimation):
         if not rolling_windows_dict or not in_sample_params:
             raise OutOfScopeStage("Kalman forecasts need rolling windows and fitted parameters (the EM fit itself is outside "
                                   "the GPU hot path); or pass sigma_forecasts= to the adapter")
-        from cvar_b200.forecast import kalman_forecast, rolling_series
+        from cvar_b200.forecast import rolling_series
         tickers = list(in_sample_params)
         windows = [np.array([w[t] for w in rolling_windows_dict.values()], dtype=float) for t in tickers]
         N = windows[0].shape[1]
-        a, l, q = ([in_sample_params[t]["optimal_params"][key] for t in tickers] for key in ("a", "l", "q"))
         series = [rolling_series(w) for w in windows]
         if all(s is not None for s in series):
-            sigma, info = kalman_forecast(np.array(series), a, l, q, N)
-        else:
-            sigma, info = kalman_forecast(np.array([w.reshape(-1) for w in windows]), a, l, q, N, window_stride=N)
+            return self.forecast_from_series(np.array(series), in_sample_params, N)
+        return self.forecast_from_series(np.array([w.reshape(-1) for w in windows]), in_sample_params, N, window_stride=N)
+
+    @staticmethod
+    def forecast_from_series(series, in_sample_params, N, window_stride=1, **_):
+        """[sigma[T, dim]] from centred return series (dim, (T-1)*window_stride + N)."""
+        from cvar_b200.forecast import kalman_forecast
+        a, l, q = ([in_sample_params[t]["optimal_params"][key] for t in in_sample_params] for key in ("a", "l", "q"))
+        sigma, info = kalman_forecast(series, a, l, q, N, window_stride=window_stride)
         if info["failed"]:
             raise FloatingPointError("the unscented filter collapsed (normalising constant <= 1e-10) in at least one window")
         return [sigma]

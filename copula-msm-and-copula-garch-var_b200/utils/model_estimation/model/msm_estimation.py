@@ -37,22 +37,43 @@ class MSMEstimation(VaRCalculationMethod):
         if not rolling_windows_dict or not in_sample_params or k is None:
             raise OutOfScopeStage("MSM forecasts need rolling windows, fitted parameters and k (fitting itself is outside "
                                   "the GPU hot path); or pass state_prob_forecasts= to the adapter")
-        from cvar_b200.forecast import MsmParams, msm_forecast, rolling_series
+        from cvar_b200.forecast import rolling_series
         tickers = list(in_sample_params)
         windows = [np.array([w[t] for w in rolling_windows_dict.values()], dtype=float) for t in tickers]
         N = windows[0].shape[1]
-        params = [MsmParams(m0=in_sample_params[t]["optimal_params"]["m_0"], sigma_bar=in_sample_params[t]["optimal_params"]["sig"],
-                            b=in_sample_params[t]["optimal_params"]["b"], gamma=in_sample_params[t]["optimal_params"]["gamma"])
-                  for t in tickers]
         series = [rolling_series(w) for w in windows]
         if all(s is not None for s in series):
-            _, _, state_probs, info = msm_forecast(np.array(series), params, int(k), N, return_state_probs=True)
-        else:   # windows that do not overlap like a rolling series: filter each one on its own
-            _, _, state_probs, info = msm_forecast(np.array([w.reshape(-1) for w in windows]), params, int(k), N,
-                                                   window_stride=N, return_state_probs=True)
+            return self.state_probs_from_series(np.array(series), in_sample_params, N, int(k))
+        # windows that do not overlap like a rolling series: filter each one on its own
+        return self.state_probs_from_series(np.array([w.reshape(-1) for w in windows]), in_sample_params, N, int(k), window_stride=N)
+
+    @staticmethod
+    def _msm_params(in_sample_params):
+        from cvar_b200.forecast import MsmParams
+        return [MsmParams(m0=v["optimal_params"]["m_0"], sigma_bar=v["optimal_params"]["sig"], b=v["optimal_params"]["b"],
+                          gamma=v["optimal_params"]["gamma"]) for v in in_sample_params.values()]
+
+    @classmethod
+    def state_probs_from_series(cls, series, in_sample_params, N, k, window_stride=1):
+        """(dim, T, 2**k) filtered state probabilities from centred return series (dim, (T-1)*window_stride + N)."""
+        from cvar_b200.forecast import msm_forecast
+        _, _, state_probs, info = msm_forecast(series, cls._msm_params(in_sample_params), k, N, window_stride=window_stride,
+                                               return_state_probs=True)
         if info["degenerate"]:
             raise FloatingPointError("MSM filter degenerated (zero normalising constant) in at least one window")
         return state_probs
+
+    @classmethod
+    def forecast_from_series(cls, series, in_sample_params, N, window_stride=1, k=None, **_):
+        """(probs_by_state[T, dim, q], sigma_states[dim, q]) straight from centred return series -- the merged layout
+        the solve consumes, produced by the filter kernel itself."""
+        from cvar_b200.forecast import msm_forecast
+        if k is None:
+            raise ValueError("MSM forecasts need k (number of multiplier components)")
+        pbs, sig, info = msm_forecast(series, cls._msm_params(in_sample_params), int(k), N, window_stride=window_stride)
+        if info["degenerate"]:
+            raise FloatingPointError("MSM filter degenerated (zero normalising constant) in at least one window")
+        return pbs, sig
 
     # ---- hot-path input layout ---------------------------------------------------------------------
     def integration_params_retrieval(self, dim, rolling_windows_dict, in_sample_params, num_points, vol_state_array):

@@ -115,3 +115,31 @@ def test_mirror_adapters_run_their_forecast_stage_on_the_gpu(fc):
     params = {"A": {"optimal_params": {"best_pq": (2, 1), "best_params": [float(g["omega"]), *g["alpha"], *g["beta"]], "best_bic": 0.0}}}
     (sigma,) = GarchEstimation().compute_forecast(windows, params)
     np.testing.assert_allclose(sigma[:, 0], g["ref"], rtol=4e-16)
+
+
+def test_from_returns_runs_returns_to_var_on_the_gpu(fc):
+    """`ValueAtRiskCalcualtion.from_returns`: centring, rolling windows, GPU forecasts, GPU solve -- against the
+    oracle pipeline fed with the reference's data-preparation rules (load_data.py:105-137)."""
+    import pandas as pd
+    from cvar_b200.inputs import make_inputs
+    from oracle import forecast_oracle as fo, var_oracle as vo
+    from utils.calc_var_class import ValueAtRiskCalcualtion
+    from utils.factory import ValueAtRiskCalculationFactory as F
+    rng = np.random.default_rng(8)
+    N, T = 120, 7
+    raw = pd.DataFrame(rng.standard_normal((N + T, 2)) * [1.0, 1.3] + [0.03, -0.02], columns=["A", "B"])
+    params = {"A": {"optimal_params": {"best_pq": (1, 1), "best_params": [0.02, 0.09, 0.89], "best_bic": 0}},
+              "B": {"optimal_params": {"best_pq": (2, 1), "best_params": [0.03, 0.05, 0.04, 0.88], "best_bic": 0}}}
+    w = np.array([0.4, 0.6])
+    v = ValueAtRiskCalcualtion.from_returns(F.create_var_calculator("gaussian", "garch"), raw, N, params, np.array([0.55]),
+                                            num_points=80, weights=w)
+    got = v.calc_var(obj_var=0.05)
+    vals = raw.to_numpy()
+    mean = vals[:N].mean(axis=0)
+    centred = vals - mean
+    sigma = np.column_stack([fo.garch_forecast(centred[:, 0], 0.02, [0.09], [0.89], N, T),
+                             fo.garch_forecast(centred[:, 1], 0.03, [0.05, 0.04], [0.88], N, T)])
+    inp = make_inputs("gaussian", "single", 80, rho=0.55, weights=w, sigma=sigma, ptf_mean=float(np.sum(mean * w)))
+    want = vo.calc_var(inp, 0.05).var
+    assert got.shape == (T,) and np.max(np.abs(got - want)) <= 1e-7
+    assert v.out_sample_N == T and len(v.out_sample_data) == T and abs(v.ptf_mean - float(np.sum(mean * w))) < 1e-15
