@@ -33,6 +33,11 @@ for _p in (str(REPO / "copula-msm-and-copula-garch-var_b200"), str(REPO)):
 METRIC = "VaR solves/sec (day x alpha)"
 UNIT = "solves/s"
 DEFAULT_WORKLOAD = "c3"
+# dram__bytes_read.sum + dram__bytes_write.sum of one solve_kernel launch, from the committed ncu --set full captures
+# (profiles/r1_c3_solve_kernel_v6_ncu_summary.txt, profiles/r1_c4_solve_kernel_v6_ncu_summary.txt); the kernel
+# reads 144 KB (c3) / 16 KB (c4) of per-day parameters plus the plan tables (c3: 0.6 MB of mixture state tables, mostly
+# L2 hits) and writes 8-16 KB of decision words that stay in L2.
+NCU_DRAM_BYTES_PER_LAUNCH = {"c3": 899328, "c4": 138496}
 WORKLOAD_DESCRIPTIONS = {
     "c1": "BASELINE configs[0]: Gaussian copula + GARCH(1,1) sigma path, n=100, 99% VaR",
     "c2": "BASELINE configs[1]: Student-t copula + GARCH(1,1), n=1024, 95%/99% VaR",
@@ -304,7 +309,7 @@ def run_b200(args, world, rank, local_rank):
         "gpu_launches": 3 * args.steps,   # per timed step: solve_kernel, finalize_reduce_kernel, finalize_apply_kernel
         "roofline": {
             "bound": "fp64", "kernel": f"solve_kernel<{inp.copula}>", "achieved": achieved_tf, "peak": peak_tf,
-            "unit": "TFLOP/s", "frac": achieved_tf / peak_tf, "traffic": None,
+            "unit": "TFLOP/s", "frac": achieved_tf / peak_tf, "traffic": NCU_DRAM_BYTES_PER_LAUNCH.get(name),
             "kernel_ms": kernel_ms, "algorithmic_flops_per_launch": flops_launch,
             "cells_per_solve_mean": float(cells_np.mean()),
             "peak_source": f"measured in this run: dependency-free DFMA micro-benchmark, {peak_ms:.0f} ms "
@@ -348,7 +353,8 @@ def main():
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD)
     ap.add_argument("--days", type=int, default=None, help="days per GPU (default: the configuration's own T)")
     ap.add_argument("--n", type=int, default=None, help="grid points per axis (default: the configuration's own n)")
-    ap.add_argument("--cpu-sample-days", type=int, default=64)
+    ap.add_argument("--cpu-sample-days", type=int, default=128,
+                    help="days of the workload the CPU port solves (cpu_baseline leg / one --impl reference step)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
