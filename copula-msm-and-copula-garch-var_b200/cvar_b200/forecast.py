@@ -111,3 +111,39 @@ def kalman_forecast(returns, a, l, q, N: int, *, window_stride: int = 1, ukf=(1.
                                                _ptr(r), T, N, window_stride, _ptr(out), C.byref(status), C.byref(ms), device)
     _lib.check(st, "cvar_kalman_forecast_host")
     return out, {"kernel_ms": ms.value, "T": T, "failed": bool(status.value)}
+
+
+def msm_forecast_device(returns, params, k: int, N: int, *, window_stride: int = 1):
+    """Device-resident variant: `returns` is a CUDA float64 tensor (n_assets, L); the filter is enqueued on torch's
+    current stream and the merged probabilities come back as a CUDA tensor (T, n_assets, q) that can be handed
+    straight to `VarPlan.solve_device` -- no host round trip between forecast and solve.
+
+    -> probs_by_state (cuda tensor), sigma_states (numpy, n_assets x q), status (cuda int32 tensor, 1 = degenerate window)
+    """
+    import torch
+
+    if not (isinstance(returns, torch.Tensor) and returns.is_cuda and returns.dtype == torch.float64 and returns.is_contiguous()):
+        raise ValueError("returns must be a contiguous CUDA float64 tensor of shape (n_assets, L)")
+    na, L = returns.shape
+    if len(params) != na or (L - N) % window_stride or L < N:
+        raise ValueError("bad shapes: one MsmParams per asset, L = (T-1)*window_stride + N")
+    T = (L - N) // window_stride + 1
+    S = 1 << k
+    dev = returns.device
+    vols = np.ascontiguousarray([msm_vol_states(k, p.m0, p.sigma_bar) for p in params])
+    stay = np.ascontiguousarray([msm_stay_probs(k, p.b, p.gamma) for p in params])
+    levels, sig = zip(*[state_levels(v) for v in vols])
+    q = len(sig[0])
+    d_vols = torch.from_numpy(vols).to(dev)
+    d_lvl = torch.from_numpy(np.ascontiguousarray(levels, dtype=np.int32)).to(dev)
+    out = torch.empty((T, na, q), dtype=torch.float64, device=dev)
+    work = torch.empty((na, L, S), dtype=torch.float64, device=dev)
+    status = torch.zeros((1,), dtype=torch.int32, device=dev)
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    with torch.cuda.device(dev):
+        st = _lib.load().cvar_msm_forecast_device(k, na, _ptr(stay), C.c_void_p(d_vols.data_ptr()), C.c_void_p(d_lvl.data_ptr()), q,
+                                                  C.c_void_p(returns.data_ptr()), T, N, window_stride, C.c_void_p(out.data_ptr()),
+                                                  None, C.c_void_p(work.data_ptr()), C.c_void_p(status.data_ptr()),
+                                                  C.c_void_p(stream))
+    _lib.check(st, "cvar_msm_forecast_device")
+    return out, np.array(sig), status

@@ -143,3 +143,24 @@ def test_from_returns_runs_returns_to_var_on_the_gpu(fc):
     want = vo.calc_var(inp, 0.05).var
     assert got.shape == (T,) and np.max(np.abs(got - want)) <= 1e-7
     assert v.out_sample_N == T and len(v.out_sample_data) == T and abs(v.ptf_mean - float(np.sum(mean * w))) < 1e-15
+
+
+def test_device_resident_forecast_feeds_the_solve_without_host_round_trip(fc, cuda_device):
+    import torch
+    from cvar_b200 import synthetic as syn
+    from cvar_b200.backend import VarPlan
+    from cvar_b200.inputs import make_inputs
+    k, N, T = 5, 90, 8
+    prm = [fc.MsmParams(0.4, 1.1, 3.0, 0.3), fc.MsmParams(0.55, 1.4, 5.0, 0.2)]
+    series = np.array([syn.msm_simulate_returns(T + N - 1, k, p.m0, p.sigma_bar, p.b, p.gamma, 60 + i) for i, p in enumerate(prm)])
+    host_pbs, host_sig, _ = fc.msm_forecast(series, prm, k, N)
+    d_pbs, sig, status = fc.msm_forecast_device(torch.from_numpy(series).to(cuda_device), prm, k, N)
+    inp = make_inputs("gaussian", "mixture", 64, rho=0.5, probs=host_pbs, sigma_states=host_sig)
+    with VarPlan(inp) as plan:
+        traj = plan.solve_device(d_pbs, [0.01])
+        var, case, iters = plan.finalize_device(traj)
+        want = plan.solve(host_pbs, [0.01])
+        torch.cuda.synchronize()
+    assert int(status.item()) == 0 and np.array_equal(sig, host_sig)
+    assert np.array_equal(d_pbs.cpu().numpy(), host_pbs)
+    assert np.array_equal(var.cpu().numpy(), want.var)
