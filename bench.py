@@ -38,6 +38,9 @@ DEFAULT_WORKLOAD = "c3"
 # reads 144 KB (c3) / 16 KB (c4) of per-day parameters plus the plan tables (c3: 0.6 MB of mixture state tables, mostly
 # L2 hits) and writes 8-16 KB of decision words that stay in L2.
 NCU_DRAM_BYTES_PER_LAUNCH = {"c3": 899328, "c4": 138496}
+# sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active from the same captures: the ISSUED-instruction view of
+# the FP64 pipe, next to the algorithmic-flop fraction (which can exceed 1)
+NCU_FP64_PIPE_PCT = {"c3": 60.2, "c4": 61.3}
 WORKLOAD_DESCRIPTIONS = {
     "c1": "BASELINE configs[0]: Gaussian copula + GARCH(1,1) sigma path, n=100, 99% VaR",
     "c2": "BASELINE configs[1]: Student-t copula + GARCH(1,1), n=1024, 95%/99% VaR",
@@ -306,11 +309,14 @@ def run_b200(args, world, rank, local_rank):
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "path": "cvar_solve_host (pinned host buffers)" if world == 1 else
                         "pinned H2D + cvar_solve_device + NCCL all-gather + cvar_finalize_device + D2H"},
-        "gpu_launches": 3 * args.steps,   # per timed step: solve_kernel, finalize_reduce_kernel, finalize_apply_kernel
+        # kernels of this repo per timed step: [order_key_kernel when the batch exceeds two waves of CTAs,] solve_kernel,
+        # finalize_reduce_kernel, finalize_apply_kernel (the radix sort of the launch order is cub's, not counted)
+        "gpu_launches": (4 if inp.T > 2 * info.sm_count * max(info.ctas_per_sm, 1) else 3) * args.steps,
         "roofline": {
             "bound": "fp64", "kernel": f"solve_kernel<{inp.copula}>", "achieved": achieved_tf, "peak": peak_tf,
             "unit": "TFLOP/s", "frac": achieved_tf / peak_tf, "traffic": NCU_DRAM_BYTES_PER_LAUNCH.get(name),
             "kernel_ms": kernel_ms, "algorithmic_flops_per_launch": flops_launch,
+            "ncu_fp64_pipe_pct_of_active_cycles": NCU_FP64_PIPE_PCT.get(name),
             "cells_per_solve_mean": float(cells_np.mean()),
             "peak_source": f"measured in this run: dependency-free DFMA micro-benchmark, {peak_ms:.0f} ms "
                            "(MEASURED_PEAKS.json has no FP64 entry; nominal 148 SM x 64 lanes x 2 x 1.965 GHz = 37.2)",

@@ -9,6 +9,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -427,8 +428,16 @@ int cvar_plan_create(const cvar_desc_t* desc, const double* x, const double* dx,
     PLAN_TRY((cudaError_t)set_smem(strip_mass_kernel<0>, p->smem_bytes));
     PLAN_TRY((cudaError_t)set_smem(strip_mass_kernel<1>, p->smem_bytes));
     PLAN_TRY((cudaError_t)set_smem(strip_mass_kernel<2>, p->smem_bytes));
+    // CTA size (measured on B200, tools/sweep_cta_threads.sh): registers cap an SM at 16 resident warps whatever the
+    // CTA size, so small grids do best with small CTAs (cheaper barriers, more days in flight): 64 threads for
+    // n in [192, 640]; tiny grids (n < 192, typically one wave of CTAs) prefer 128 threads for their axis stage;
+    // from there 256 threads while two CTAs fit an SM's shared memory, 512 when only one does.
     int occ = 0;
-    p->cta_threads = CTA_THREADS_SMALL;
+    p->cta_threads = n < 192 ? 128 : n <= 640 ? 64 : CTA_THREADS_SMALL;
+    if (const char* env = std::getenv("CVAR_CTA_THREADS")) {   // tuning knob: 32..512, multiple of 32
+        const int v = std::atoi(env);
+        if (v >= 32 && v <= CTA_THREADS_LARGE && v % 32 == 0) p->cta_threads = v;
+    }
     for (int attempt = 0; attempt < 2; ++attempt) {
         switch (desc->copula) {
             case CVAR_COPULA_GAUSSIAN: PLAN_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, solve_kernel<0>, p->cta_threads, p->smem_bytes)); break;

@@ -126,7 +126,8 @@ template <int COPULA>
 __device__ void stage0(const KernelParams& P, const double* __restrict__ dayp, const Smem& S) {
     const int n = P.n, q = P.q;
     if (threadIdx.x < 4) S.live[threadIdx.x] = 0;
-    if (COPULA == 1 && threadIdx.x < LOGTAB_SIZE) S.ltab[threadIdx.x] = P.logtab[threadIdx.x];
+    if (COPULA == 1)
+        for (int k = threadIdx.x; k < LOGTAB_SIZE; k += blockDim.x) S.ltab[k] = P.logtab[k];
     if (COPULA != 2)
         for (int k = threadIdx.x; k < EXPTAB_SIZE; k += blockDim.x) S.etab[k] = P.exptab[k];
     __syncthreads();

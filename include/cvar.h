@@ -68,7 +68,8 @@ extern "C" {
 #define CVAR_ERR_ABI (-7)           /* struct_size / abi_version mismatch                */
 #define CVAR_ERR_SMEM (-8)          /* grid too large for the shared memory of one SM    */
 
-#define CVAR_MAX_N 8192
+#define CVAR_MAX_N 8192 /* hard cap; this version keeps a day's axis data in one SM's shared memory, which
+                           limits n to ~4200 on B200 (cvar_plan_create returns CVAR_ERR_SMEM beyond) */
 #define CVAR_MAX_Q 32
 #define CVAR_MAX_ALPHA 8
 #define CVAR_MAX_ITER 30

@@ -140,6 +140,10 @@ def test_error_paths(gpu):
             plan.solve(inp.day_params(), [0.01], forced_iterations=40)
         empty = plan.solve(np.empty((0, 2)), [0.01])
         assert empty.var.shape == (1, 0)
+    huge = make_inputs("gaussian", "single", 5000, sigma=np.ones((1, 2)))       # beyond one SM's shared memory
+    with pytest.raises(CvarError) as e:
+        VarPlan(huge)
+    assert e.value.status == -8
     bad = make_inputs("gaussian", "single", 64, rho=1.5, sigma=np.ones((3, 2)))
     with pytest.raises(CvarError) as e:
         VarPlan(bad)
