@@ -172,6 +172,7 @@ def run_reference(args, world, rank):
     sample = list(range(0, inp_all.T, max(1, inp_all.T // args.cpu_sample_days)))[: args.cpu_sample_days]
     pool = make_pool(workers)
     try:
+        cpu_port_solve(inp_all, alphas[:1], sample[:workers], None, pool, workers)     # spawn + import the workers (untimed)
         for _ in range(args.warmup):
             cpu_port_solve(inp_all, alphas[:1], sample[:workers], None, pool, workers)
         t = 0.0
@@ -201,7 +202,7 @@ def run_b200(args, world, rank, local_rank):
     import torch.distributed as dist
     from cvar_b200.backend import VarPlan, fp64_peak_tflops
     from cvar_b200.distributed import solve_sharded
-    from oracle import var_oracle as vo          # work model constants + the cpu_baseline leg only
+    from cvar_b200.workmodel import algorithmic_flops
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the VaR backend has no CPU fallback")
@@ -259,8 +260,7 @@ def run_b200(args, world, rank, local_rank):
     plan.solve_device(d_day, alphas, traj=traj, cells=cells)
     torch.cuda.synchronize()
     cells_np = cells.cpu().numpy()
-    flops_launch = float(vo.F_CELL[inp.copula]) * float(cells_np.sum()) + \
-        na * inp.T * 2.0 * inp.n * vo.flops_per_axis_point(inp.copula, inp.marginal, inp.q)
+    flops_launch = algorithmic_flops(inp.copula, inp.marginal, inp.q, inp.n, cells_np)
     achieved_tf = flops_launch / (kernel_ms * 1e-3) / 1e12
     peak_tf, peak_ms = fp64_peak_tflops(local_rank, 100.0)
 
@@ -328,6 +328,7 @@ def run_b200(args, world, rank, local_rank):
 
     # ---- cpu_baseline + parity on a bounded sample (rank 0, N = 1 only) ---------------------------------
     if world == 1 and args.cpu_sample_days > 0:
+        from cvar_b200.backtest import exceedances      # the oracle itself is only executed inside the worker processes
         workers = len(os.sched_getaffinity(0))
         sample = list(range(0, inp.T, max(1, inp.T // args.cpu_sample_days)))[: args.cpu_sample_days]
         forced = [int(k) for k in iters.cpu().numpy()]
@@ -341,7 +342,7 @@ def run_b200(args, world, rank, local_rank):
         max_dvar = max(float(np.max(np.abs(gpu_var[k][sample] - cpu_var[a]))) for k, a in enumerate(alphas))
         rng = np.random.default_rng(11)
         r_ptf = rng.standard_normal(len(sample)) * 1.2
-        exc_equal = all(vo.exceedances(gpu_var[k][sample], r_ptf) == vo.exceedances(cpu_var[a], r_ptf)
+        exc_equal = all(exceedances(gpu_var[k][sample], r_ptf) == exceedances(cpu_var[a], r_ptf)
                         for k, a in enumerate(alphas))
         out["cpu_baseline"] = {"value": len(sample) * na / dt, "unit": UNIT, "cores": workers, "kind": "port",
                                "sample": f"{len(sample)} of {inp.T} days x {na} alpha(s), n={inp.n}, {dt:.1f} s wall"}

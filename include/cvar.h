@@ -20,6 +20,8 @@
  *   - `*_device` entry points take DEVICE pointers owned by the caller (e.g.
  *     torch tensors on the plan's device), enqueue on the given cudaStream_t
  *     (passed as void*; NULL = the legacy default stream) and do not synchronise.
+ *   - a plan owns scratch buffers (launch order, iteration counts, host-path workspace): calls on ONE plan must not
+ *     overlap in time (use one plan per concurrent stream / thread); different plans are independent.
  *   - there is no CPU fallback: without a CUDA device plan creation fails.
  *   - all floating-point data is IEEE binary64.  Two-asset portfolios (dim = 2).
  */

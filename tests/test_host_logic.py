@@ -155,3 +155,14 @@ def test_shard_bounds_cover_all_days_once():
         assert spans[0][0] == 0 and spans[-1][1] == T
         assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
         assert max(hi - lo for lo, hi in spans) <= -(-T // world) if T else True
+
+
+def test_work_model_matches_survey_figures():
+    from cvar_b200 import workmodel as wm
+    from oracle import var_oracle as vo
+    assert wm.F_CELL == vo.F_CELL and wm.F_AXIS_SINGLE == vo.F_AXIS_SINGLE
+    assert wm.flops_per_axis_point("student", "mixture", 9) == 2612 + 78 * 9 - 80
+    # SURVEY worked example: n = 2048, Student + single-normal, C = 0.382 n^2  ->  ~1.39e8 flop per solve
+    c = 0.382 * 2048 ** 2
+    assert abs(wm.algorithmic_flops("student", "single", 1, 2048, [c]) - 1.39e8) < 0.02e8
+    assert wm.algorithmic_flops("gaussian", "single", 1, 100, [10, 20]) == 35 * 30 + 2 * 2 * 100 * 262
