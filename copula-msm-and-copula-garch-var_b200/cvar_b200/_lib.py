@@ -77,7 +77,8 @@ def load(path: str | Path | None = None):
     global _lib
     if _lib is not None and path is None:
         return _lib
-    p = Path(path) if path else LIB_PATH
+    import os
+    p = Path(path) if path else Path(os.environ.get("CVAR_B200_LIB", LIB_PATH))    # env override: A/B-test another build
     if not p.exists():
         raise ImportError(
             f"{p} is missing: build it with `python __graft_entry__.py` (nvcc, sm_100a). "
