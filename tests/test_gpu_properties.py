@@ -80,6 +80,30 @@ def test_full_size_days_agree_with_the_oracle(backend, name, n, T):
         assert np.array_equal(res.case[k], tr.case)
 
 
+@pytest.mark.parametrize("name", ["c5_student_mixture", "c5_gaussian_single", "c5_plackett_single"])
+def test_4096_grid_uses_the_512_thread_layout_and_agrees_with_the_oracle(backend, name):
+    """n = 4096 only fits one CTA per SM, which switches the kernel to 512-thread CTAs: same answers required."""
+    from oracle import var_oracle as vo
+    inp, alphas = _inputs(name, 4096, 2)
+    with backend.VarPlan(inp) as plan:
+        info = plan.info()
+        res = plan.solve(inp.day_params(), alphas)
+        strips = plan.strip_mass(inp.day_params(), np.array([[-100.0, -1.5], [-2.0, -1.0]]))
+    assert (info.threads_per_cta, info.ctas_per_sm) == (512, 1)
+    np.testing.assert_allclose(strips, vo.compute_integral(inp, np.array([[-100.0, -1.5], [-2.0, -1.0]])), rtol=2e-12, atol=2e-13)
+    for k, a in enumerate(alphas):
+        tr = vo.calc_var(inp, a)
+        assert res.iterations[k] == tr.iterations
+        assert res.var[k].tobytes() == tr.var.tobytes()
+
+
+def test_small_grids_use_small_ctas(backend):
+    from cvar_b200.inputs import make_inputs
+    for n, threads in ((100, 128), (256, 64), (600, 64), (1024, 256), (2048, 256)):
+        with backend.VarPlan(make_inputs("gaussian", "single", n, sigma=np.ones((1, 2)))) as plan:
+            assert plan.info().threads_per_cta == threads
+
+
 def test_mass_is_monotone_in_the_quantile(backend):
     inp, _ = _inputs("c2", 1024, 4)
     qs = np.linspace(-6.0, 2.0, 33)
