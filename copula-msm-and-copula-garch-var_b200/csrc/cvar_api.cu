@@ -40,6 +40,8 @@ struct cvar_plan {
     double* d_tq_table;
     double* d_logtab;
     double* d_exptab;
+    double* d_powtab;
+    int kernel_variant;  // KV_* template instantiation used by this plan
     double* d_state_cdf;
     double* d_state_pdf;
     // growable workspace of the *_host entry points
@@ -153,16 +155,13 @@ int launch_solve(cvar_plan* p, const double* d_day, int64_t T, const AlphaSet& A
     int rc = make_order(p, d_day, T, st, &order);
     if (rc) return rc;
     dim3 grid((unsigned)T), block(p->cta_threads);
-    switch (p->desc.copula) {
-        case CVAR_COPULA_GAUSSIAN:
-            solve_kernel<0><<<grid, block, p->smem_bytes, st>>>(p->kp, d_day, (long long)T, A, order, d_traj, d_mass, d_cells);
-            break;
-        case CVAR_COPULA_STUDENT:
-            solve_kernel<1><<<grid, block, p->smem_bytes, st>>>(p->kp, d_day, (long long)T, A, order, d_traj, d_mass, d_cells);
-            break;
-        default:
-            solve_kernel<2><<<grid, block, p->smem_bytes, st>>>(p->kp, d_day, (long long)T, A, order, d_traj, d_mass, d_cells);
+#define CVAR_LAUNCH_SOLVE(KV) \
+    case KV: solve_kernel<KV><<<grid, block, p->smem_bytes, st>>>(p->kp, d_day, (long long)T, A, order, d_traj, d_mass, d_cells); break;
+    switch (p->kernel_variant) {
+        CVAR_LAUNCH_SOLVE(0) CVAR_LAUNCH_SOLVE(1) CVAR_LAUNCH_SOLVE(2) CVAR_LAUNCH_SOLVE(3) CVAR_LAUNCH_SOLVE(4) CVAR_LAUNCH_SOLVE(5)
+        default: return CVAR_ERR_COPULA;
     }
+#undef CVAR_LAUNCH_SOLVE
     return (int)cudaGetLastError();
 }
 
@@ -170,16 +169,13 @@ int launch_strip(cvar_plan* p, const double* d_day, int64_t T, const double* d_b
                  unsigned long long* d_cells, cudaStream_t st) {
     if (T == 0) return 0;
     dim3 grid((unsigned)T), block(p->cta_threads);
-    switch (p->desc.copula) {
-        case CVAR_COPULA_GAUSSIAN:
-            strip_mass_kernel<0><<<grid, block, p->smem_bytes, st>>>(p->kp, d_day, d_bounds, d_out, d_cells);
-            break;
-        case CVAR_COPULA_STUDENT:
-            strip_mass_kernel<1><<<grid, block, p->smem_bytes, st>>>(p->kp, d_day, d_bounds, d_out, d_cells);
-            break;
-        default:
-            strip_mass_kernel<2><<<grid, block, p->smem_bytes, st>>>(p->kp, d_day, d_bounds, d_out, d_cells);
+#define CVAR_LAUNCH_STRIP(KV) \
+    case KV: strip_mass_kernel<KV><<<grid, block, p->smem_bytes, st>>>(p->kp, d_day, d_bounds, d_out, d_cells); break;
+    switch (p->kernel_variant) {
+        CVAR_LAUNCH_STRIP(0) CVAR_LAUNCH_STRIP(1) CVAR_LAUNCH_STRIP(2) CVAR_LAUNCH_STRIP(3) CVAR_LAUNCH_STRIP(4) CVAR_LAUNCH_STRIP(5)
+        default: return CVAR_ERR_COPULA;
     }
+#undef CVAR_LAUNCH_STRIP
     return (int)cudaGetLastError();
 }
 
@@ -299,7 +295,25 @@ int cvar_plan_create(const cvar_desc_t* desc, const double* x, const double* dx,
     int rc = (int)cudaGetDeviceProperties(&prop, device);
     if (rc) { delete p; return rc; }
     p->sm_count = prop.multiProcessorCount;
-    p->smem_bytes = smem_bytes_for(n);
+    // kernel variant: Student-t cells use the table-assisted power when its binomial series converges fast enough
+    // for this nu (degree <= 13 for a truncation error below 1e-17), else the generic log2/exp2 cell
+    p->kernel_variant = desc->copula;
+    double powc[POW_MAX_DEG + 2] = {0};
+    if (desc->copula == CVAR_COPULA_STUDENT && !std::getenv("CVAR_STUDENT_GENERIC")) {
+        const double c = 0.5 * (desc->nu + 2.0), fmax_ = std::ldexp(1.03, -8);
+        powc[0] = 1.0;
+        int need = -1;
+        double pw = 1.0;
+        for (int k = 1; k <= POW_MAX_DEG + 1; ++k) {
+            powc[k] = powc[k - 1] * (-(c + k - 1)) / k;   // binom(-c, k)
+            pw *= fmax_;
+            if (need < 0 && std::fabs(powc[k]) * pw < 1e-17) need = k - 1;   // first neglected term is small enough
+        }
+        if (need >= 0 && need <= 7) p->kernel_variant = KV_STUDENT_POW7;
+        else if (need >= 0 && need <= 10) p->kernel_variant = KV_STUDENT_POW10;
+        else if (need >= 0 && need <= 13) p->kernel_variant = KV_STUDENT_POW13;
+    }
+    p->smem_bytes = smem_bytes_for(n, p->kernel_variant);
     if (p->smem_bytes > (size_t)prop.sharedMemPerBlockOptin) { delete p; return CVAR_ERR_SMEM; }
 
     // ---- run constants -------------------------------------------------------------------
@@ -418,16 +432,16 @@ int cvar_plan_create(const cvar_desc_t* desc, const double* x, const double* dx,
         logtab_build_kernel<<<1, LOGTAB_SIZE, 0, p->stream>>>(kp.negc, p->d_logtab);
         PLAN_TRY(cudaGetLastError());
         kp.logtab = p->d_logtab;
+        for (int k = 0; k <= POW_MAX_DEG; ++k) kp.powc[k] = powc[k];
+        PLAN_TRY(cudaMalloc(&p->d_powtab, sizeof(double) * (POW_MTAB + POW_ETAB)));
+        powtab_build_kernel<<<1, POW_MTAB, 0, p->stream>>>(0.5 * (desc->nu + 2.0), p->d_powtab);
+        PLAN_TRY(cudaGetLastError());
+        kp.powtab = p->d_powtab;
     }
     PLAN_TRY(cudaStreamSynchronize(p->stream));
 
     // opt in to the dynamic shared memory this grid needs, for every instantiation
-    PLAN_TRY((cudaError_t)set_smem(solve_kernel<0>, p->smem_bytes));
-    PLAN_TRY((cudaError_t)set_smem(solve_kernel<1>, p->smem_bytes));
-    PLAN_TRY((cudaError_t)set_smem(solve_kernel<2>, p->smem_bytes));
-    PLAN_TRY((cudaError_t)set_smem(strip_mass_kernel<0>, p->smem_bytes));
-    PLAN_TRY((cudaError_t)set_smem(strip_mass_kernel<1>, p->smem_bytes));
-    PLAN_TRY((cudaError_t)set_smem(strip_mass_kernel<2>, p->smem_bytes));
+    // opt in to the dynamic shared memory this grid needs (for the instantiation this plan uses) and size the CTAs.
     // CTA size (measured on B200, tools/sweep_cta_threads.sh): registers cap an SM at 16 resident warps whatever the
     // CTA size, so small grids do best with small CTAs (cheaper barriers, more days in flight): 64 threads for
     // n in [192, 640]; tiny grids (n < 192, typically one wave of CTAs) prefer 128 threads for their axis stage;
@@ -438,15 +452,21 @@ int cvar_plan_create(const cvar_desc_t* desc, const double* x, const double* dx,
         const int v = std::atoi(env);
         if (v >= 32 && v <= CTA_THREADS_LARGE && v % 32 == 0) p->cta_threads = v;
     }
-    for (int attempt = 0; attempt < 2; ++attempt) {
-        switch (desc->copula) {
-            case CVAR_COPULA_GAUSSIAN: PLAN_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, solve_kernel<0>, p->cta_threads, p->smem_bytes)); break;
-            case CVAR_COPULA_STUDENT: PLAN_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, solve_kernel<1>, p->cta_threads, p->smem_bytes)); break;
-            default: PLAN_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, solve_kernel<2>, p->cta_threads, p->smem_bytes));
-        }
-        if (occ >= 2 || attempt == 1) break;
-        p->cta_threads = CTA_THREADS_LARGE;   // only one CTA fits an SM: give it 16 warps
+#define CVAR_PREP(KV)                                                                                              \
+    case KV:                                                                                                       \
+        PLAN_TRY((cudaError_t)set_smem(solve_kernel<KV>, p->smem_bytes));                                          \
+        PLAN_TRY((cudaError_t)set_smem(strip_mass_kernel<KV>, p->smem_bytes));                                     \
+        for (int attempt = 0; attempt < 2; ++attempt) {                                                            \
+            PLAN_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, solve_kernel<KV>, p->cta_threads, p->smem_bytes)); \
+            if (occ >= 2 || attempt == 1) break;                                                                   \
+            p->cta_threads = CTA_THREADS_LARGE; /* only one CTA fits an SM: give it 16 warps */                    \
+        }                                                                                                          \
+        break;
+    switch (p->kernel_variant) {
+        CVAR_PREP(0) CVAR_PREP(1) CVAR_PREP(2) CVAR_PREP(3) CVAR_PREP(4) CVAR_PREP(5)
+        default: break;
     }
+#undef CVAR_PREP
     p->ctas_per_sm = occ;
 #undef PLAN_TRY
     *out = p;
@@ -463,6 +483,7 @@ int cvar_plan_destroy(cvar_plan_t* p) {
     cudaFree(p->d_tq_table);
     cudaFree(p->d_logtab);
     cudaFree(p->d_exptab);
+    cudaFree(p->d_powtab);
     cudaFree(p->d_state_cdf);
     cudaFree(p->d_state_pdf);
     cudaFree(p->d_ws);

@@ -24,6 +24,14 @@ namespace cvar {
 constexpr int CTA_THREADS_SMALL = 256;
 constexpr int CTA_THREADS_LARGE = 512;
 constexpr int MAX_CTA_WARPS = CTA_THREADS_LARGE / 32;
+// Kernel variants (template parameter COPULA of the kernels below): the three copula families plus three
+// Student-t variants whose cell uses the table-assisted power with a binomial series of fixed degree.
+constexpr int KV_GAUSSIAN = 0, KV_STUDENT = 1, KV_PLACKETT = 2, KV_STUDENT_POW7 = 3, KV_STUDENT_POW10 = 4, KV_STUDENT_POW13 = 5;
+__host__ __device__ constexpr bool kv_is_student(int kv) { return kv == KV_STUDENT || kv >= KV_STUDENT_POW7; }
+__host__ __device__ constexpr int kv_pow_degree(int kv) {
+    return kv == KV_STUDENT_POW7 ? 7 : kv == KV_STUDENT_POW10 ? 10 : kv == KV_STUDENT_POW13 ? 13 : 0;
+}
+
 // independent cells per thread per loop trip (FP64 latency hiding); the cheap cells need more of them
 #ifndef CVAR_CIF_GAUSSIAN
 #define CVAR_CIF_GAUSSIAN 8
@@ -36,7 +44,7 @@ constexpr int MAX_CTA_WARPS = CTA_THREADS_LARGE / 32;
 #endif
 template <int COPULA>
 struct CellsInFlight {
-    static constexpr int value = COPULA == 0 ? CVAR_CIF_GAUSSIAN : (COPULA == 1 ? CVAR_CIF_STUDENT : CVAR_CIF_PLACKETT);
+    static constexpr int value = COPULA == 0 ? CVAR_CIF_GAUSSIAN : (kv_is_student(COPULA) ? CVAR_CIF_STUDENT : CVAR_CIF_PLACKETT);
 };
 
 typedef unsigned short u16;
@@ -63,6 +71,8 @@ struct KernelParams {
     double qc[CVAR_LOG2_1P_POLY_DEG + 1];  // student: negc * coefficients of log2(1+f)/f
     const double* logtab;  // student: negc * (-log2 r_i), LOGTAB_SIZE entries (global; staged to shared memory)
     const double* exptab;  // gaussian / student: 2^(i/256), EXPTAB_SIZE entries (global; staged to shared memory)
+    double powc[POW_MAX_DEG + 1];  // student pow variants: binomial coefficients of (1+f)^(-(nu+2)/2)
+    const double* powtab;  // student pow variants: r_i^c (POW_MTAB) then 2^(-c e) (POW_ETAB)
     const double* x;
     const double* dx;
     const double* sigma_states;  // [2][q] or nullptr
@@ -90,14 +100,24 @@ struct Smem {
     double* ltab;   // [LOGTAB_SIZE] student only
     double* etab;   // [EXPTAB_SIZE] gaussian / student
     double* memo;   // [MEMO_SIZE][4]: (lo, hi, mass, cells) of strips already integrated for an earlier alpha
+    double* ptab;   // [POW_MTAB + POW_ETAB] student pow variants (aliases the ltab/etab region)
 };
 
-__host__ __device__ inline size_t smem_bytes_for(int n) {
-    size_t npad = (size_t)((n + 3) & ~3);
-    return npad * 8 * 6 + npad * 2 * 3 + 2 * MAX_CTA_WARPS * 8 + 2 * MAX_CTA_WARPS * 4 + 16 + 64 + LOGTAB_SIZE * 8 + EXPTAB_SIZE * 8 + MEMO_SIZE * 4 * 8;
+// doubles of per-variant lookup tables staged in shared memory (after the fixed part)
+__host__ __device__ constexpr int table_doubles(int kv) {
+    return kv == KV_GAUSSIAN ? EXPTAB_SIZE
+         : kv == KV_STUDENT  ? LOGTAB_SIZE + EXPTAB_SIZE
+         : kv == KV_PLACKETT ? 0
+                             : POW_MTAB + POW_ETAB;
 }
 
-__device__ __forceinline__ Smem carve(unsigned char* base, int n) {
+__host__ __device__ inline size_t smem_bytes_for(int n, int kv) {
+    size_t npad = (size_t)((n + 3) & ~3);
+    return npad * 8 * 6 + npad * 2 * 3 + 2 * MAX_CTA_WARPS * 8 + 2 * MAX_CTA_WARPS * 4 + 16 + 64 + MEMO_SIZE * 4 * 8 +
+           (size_t)table_doubles(kv) * 8;
+}
+
+__device__ __forceinline__ Smem carve(unsigned char* base, int n, int kv) {
     size_t npad = (size_t)((n + 3) & ~3);
     Smem S;
     double* d = reinterpret_cast<double*>(base);
@@ -113,9 +133,11 @@ __device__ __forceinline__ Smem carve(unsigned char* base, int n) {
     S.c[2] = h + 2 * npad;
     S.redc = reinterpret_cast<unsigned*>(h + 3 * npad);
     S.live = reinterpret_cast<int*>(S.redc + 2 * MAX_CTA_WARPS);
-    S.ltab = reinterpret_cast<double*>(S.live + 4 + 12);  // 64 bytes after `live`: stays 8-byte aligned
-    S.etab = S.ltab + LOGTAB_SIZE;
-    S.memo = S.etab + EXPTAB_SIZE;
+    S.memo = reinterpret_cast<double*>(S.live + 4 + 12);  // 64 bytes after `live`: stays 8-byte aligned
+    double* tables = S.memo + MEMO_SIZE * 4;              // variant-specific tables, see table_doubles()
+    S.ltab = tables;                                      // KV_STUDENT: ltab then etab
+    S.etab = kv == KV_STUDENT ? tables + LOGTAB_SIZE : tables;
+    S.ptab = tables;
     return S;
 }
 
@@ -126,10 +148,12 @@ template <int COPULA>
 __device__ void stage0(const KernelParams& P, const double* __restrict__ dayp, const Smem& S) {
     const int n = P.n, q = P.q;
     if (threadIdx.x < 4) S.live[threadIdx.x] = 0;
-    if (COPULA == 1)
+    if (COPULA == KV_STUDENT)
         for (int k = threadIdx.x; k < LOGTAB_SIZE; k += blockDim.x) S.ltab[k] = P.logtab[k];
-    if (COPULA != 2)
+    if (COPULA == KV_GAUSSIAN || COPULA == KV_STUDENT)
         for (int k = threadIdx.x; k < EXPTAB_SIZE; k += blockDim.x) S.etab[k] = P.exptab[k];
+    if (kv_pow_degree(COPULA) > 0)
+        for (int k = threadIdx.x; k < POW_MTAB + POW_ETAB; k += blockDim.x) S.ptab[k] = P.powtab[k];
     __syncthreads();
     const bool swap = (P.compat & 1u) != 0;
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
@@ -193,7 +217,10 @@ __device__ void stage0(const KernelParams& P, const double* __restrict__ dayp, c
                 const double hp = 0.5 * (P.nu + 1.0);
                 const double c1 = 1.0 + y[1] * y[1] / P.nu;
                 const double c0 = 1.0 + y[0] * y[0] / P.nu;
-                S.in[i] = make_double2(P.g_in_scale * y[1], fmax(l1 + hp * log2(c1), -1100.0));
+                if (kv_pow_degree(COPULA) > 0)   // the power variants multiply by the column weight instead of adding its log
+                    S.in[i] = make_double2(P.g_in_scale * y[1], a[1] * exp2(hp * log2(c1)));
+                else
+                    S.in[i] = make_double2(P.g_in_scale * y[1], fmax(l1 + hp * log2(c1), -1100.0));
                 S.out0[i] = P.g_out_scale * y[0];
                 S.out1[i] = c0;
                 S.out2[i] = a[0] * P.g_const * exp2(hp * log2(c0));
@@ -298,6 +325,24 @@ struct Row<1> {  // Student-t: W = rowfac * 2^( l1[j] - (nu+2)/2 * log2( c0 + (y
         return exp2_tab(scaled_log2_plus(t, b, P.negc, P.qc, S.ltab), S.etab);
     }
 };
+
+template <int DEG>
+struct RowStudentPow {  // Student-t: W = rowfac * A1[j] * ( c0 + (y1'[j] - m0)^2 )^(-(nu+2)/2), table-assisted power
+    double m0, c0, fac;
+    __device__ __forceinline__ void load(const KernelParams&, const Smem& S, int i) {
+        m0 = S.out0[i];
+        c0 = S.out1[i];
+        fac = S.out2[i];
+    }
+    __device__ __forceinline__ double cell(const KernelParams& P, const Smem& S, double a, double b) const {
+        const double d = a - m0;
+        const double t = fma(d, d, c0);  // >= 1
+        return b * pow_neg_c<DEG>(t, P.powc, S.ptab);
+    }
+};
+template <> struct Row<KV_STUDENT_POW7> : RowStudentPow<7> {};
+template <> struct Row<KV_STUDENT_POW10> : RowStudentPow<10> {};
+template <> struct Row<KV_STUDENT_POW13> : RowStudentPow<13> {};
 
 template <>
 struct Row<2> {  // Plackett (the reference's formula, plackett.py:66-69), u = row, v = column
@@ -465,7 +510,7 @@ solve_kernel(KernelParams P, const double* __restrict__ day_params, long long T,
              const int* __restrict__ order, unsigned* __restrict__ traj, double* __restrict__ mass_out,
              unsigned long long* __restrict__ cells_out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const Smem S = carve(smem_raw, P.n);
+    const Smem S = carve(smem_raw, P.n, COPULA);
     // CTAs are dispatched in block-index order; `order` lists the days most expensive first (see order_key_kernel)
     const long long day = order ? order[blockIdx.x] : blockIdx.x;
     const int stride = (P.marginal == 0) ? 2 : 2 * P.q;
@@ -566,7 +611,7 @@ __global__ void __launch_bounds__(CTA_THREADS_LARGE, 1)
 strip_mass_kernel(KernelParams P, const double* __restrict__ day_params, const double* __restrict__ bounds,
                   double* __restrict__ out, unsigned long long* __restrict__ cells_out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const Smem S = carve(smem_raw, P.n);
+    const Smem S = carve(smem_raw, P.n, COPULA);
     const long long day = blockIdx.x;
     const int stride = (P.marginal == 0) ? 2 : 2 * P.q;
     stage0<COPULA>(P, day_params + day * stride, S);

@@ -134,6 +134,37 @@ __device__ __forceinline__ double scaled_log2_plus(double t, double b, double c,
     return fma(f, q, base);
 }
 
+// ----- table-assisted  t^(-c)  for the Student-t cell (no log, no exp) ---------------------------------
+// With t = 2^e * m and r_i the seed reciprocal of m's interval midpoint, m = (1 + f) / r_i, so
+//     t^(-c) = 2^(-c e) * r_i^c * (1 + f)^(-c).
+// 2^(-c e) and r_i^c come from two small per-plan tables (POW_ETAB + POW_MTAB doubles in shared memory) and
+// (1 + f)^(-c) is its binomial series in f (|f| <= 2^-8), whose degree the plan picks from c:
+// 1 + DEG + 2 FP64 instructions in total instead of ~17 for c*log2(t) followed by exp2.
+constexpr int POW_MTAB = LOGTAB_SIZE;  // same mantissa intervals and seed reciprocals as the log2 table
+constexpr int POW_ETAB = 64;           // exponents 0..63 (t >= 1 always: t = C0 + d^2)
+constexpr int POW_MAX_DEG = 13;
+
+__global__ void powtab_build_kernel(double c, double* __restrict__ tab) {
+    const int i = threadIdx.x;
+    if (i < POW_MTAB) tab[i] = pow(logtab_recip(i), c);
+    if (i < POW_ETAB) tab[POW_MTAB + i] = exp2(-c * (double)i);
+}
+
+template <int DEG>
+__device__ __forceinline__ double pow_neg_c(double t, const double* __restrict__ kc, const double* __restrict__ tab) {
+    const int hi = __double2hiint(t);
+    const int e = (hi >> 20) - 1023;
+    const int idx = (hi >> (20 - LOGTAB_BITS)) & (POW_MTAB - 1);
+    double r = logtab_recip(idx);
+    r = __hiloint2double(__double2hiint(r) - (e << 20), 0);  // r_i * 2^-e
+    const double f = fma(t, r, -1.0);
+    double p = kc[DEG];
+#pragma unroll
+    for (int k = DEG - 1; k >= 1; --k) p = fma(p, f, kc[k]);
+    p = fma(p, f, 1.0);
+    return (tab[idx] * tab[POW_MTAB + min(e, POW_ETAB - 1)]) * p;
+}
+
 // ---------------------------------------------------------------------------------------------
 // per-axis-point functions
 // ---------------------------------------------------------------------------------------------
