@@ -313,7 +313,7 @@ def run_b200(args, world, rank, local_rank):
         # finalize_reduce_kernel, finalize_apply_kernel (the radix sort of the launch order is cub's, not counted)
         "gpu_launches": (4 if inp.T > 2 * info.sm_count * max(info.ctas_per_sm, 1) else 3) * args.steps,
         "roofline": {
-            "bound": "fp64", "kernel": f"solve_kernel<{inp.copula}>", "achieved": achieved_tf, "peak": peak_tf,
+            "bound": "fp64", "kernel": f"solve_kernel<{info.kernel_variant}> ({inp.copula})", "achieved": achieved_tf, "peak": peak_tf,
             "unit": "TFLOP/s", "frac": achieved_tf / peak_tf, "traffic": NCU_DRAM_BYTES_PER_LAUNCH.get(name),
             "kernel_ms": kernel_ms, "algorithmic_flops_per_launch": flops_launch,
             "ncu_fp64_pipe_pct_of_active_cycles": NCU_FP64_PIPE_PCT.get(name),
@@ -323,7 +323,8 @@ def run_b200(args, world, rank, local_rank):
         },
         "iterations": [int(k) for k in iters.cpu().numpy()],
         "plan": {"ctas_per_sm": info.ctas_per_sm, "threads_per_cta": info.threads_per_cta,
-                 "smem_bytes_per_cta": info.smem_bytes_per_cta, "sm_count": info.sm_count},
+                 "smem_bytes_per_cta": info.smem_bytes_per_cta, "sm_count": info.sm_count,
+                 "kernel_variant": info.kernel_variant},
     }
 
     # ---- cpu_baseline + parity on a bounded sample (rank 0, N = 1 only) ---------------------------------

@@ -506,6 +506,8 @@ int cvar_plan_get_info(const cvar_plan_t* p, cvar_plan_info_t* info) {
     info->smem_bytes_per_cta = (int32_t)p->smem_bytes;
     info->tq_table_max_rel_err = p->tq_err;
     info->last_kernel_ms = p->last_kernel_ms;
+    info->kernel_variant = p->kernel_variant;
+    info->reserved = 0;
     return CVAR_OK;
 }
 
