@@ -16,6 +16,10 @@ GOLDEN_DIR = REPO / "tests" / "golden"
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    # the CUDA library is a build artefact (git-ignored): compile it if this checkout does not have it yet
+    from cvar_b200.build import LIB_PATH, build_library
+    if not LIB_PATH.exists():
+        build_library()
 
 
 NON_SOLVE_GOLDENS = {"forecast_producers"}
