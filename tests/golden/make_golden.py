@@ -133,6 +133,10 @@ def build_cases():
     add("student_garch_n256_T3", "student", "single", 256, sigma=syn.garch_sigma_path(3), alphas=(0.01,))
     add("plackett_mr_n1024_T2", "plackett", "single", 1024, est="mean_reverting", sigma=syn.kalman_sigma_path(2),
         alphas=(0.05,), strips=False)
+    add("student_garch_n512_T2", "student", "single", 512, sigma=syn.garch_sigma_path(2), alphas=(0.01, 0.05), nu=5.3, rho=0.6)
+    add("gaussian_garch_n1024_T2", "gaussian", "single", 1024, sigma=syn.garch_sigma_path(2), alphas=(0.01,), strips=False)
+    add("student_msm8_n96_T2", "student", "mixture", 96, vs_probs=_msm8(2), alphas=(0.01, 0.05))
+    add("plackett_msm8_n96_w64", "plackett", "mixture", 96, vs_probs=_msm8(2), weights=(0.6, 0.4), alphas=(0.01,))
     return cases
 
 
