@@ -361,7 +361,7 @@ struct Row<2> {  // Plackett (the reference's formula, plackett.py:66-69), u = r
         const double pp = fma(eta, v, p0);
         const double rr = fma(-eta, v, r0);
         const double dd = pp * rr;
-        return (a1 * num) * rcp_fast(dd * dd);
+        return (a1 * num) * rcp_cell(dd * dd);
     }
 };
 

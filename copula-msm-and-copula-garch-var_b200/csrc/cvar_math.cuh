@@ -73,6 +73,14 @@ __device__ __forceinline__ double rcp_fast(double a) {
     return r;
 }
 
+// 1/a with ONE Newton step on the 2^-23 seed: relative error e0^2 <= 1.4e-14, always of the same sign.  Enough for
+// a cell weight (budget 1e-13 relative), and two FP64 instructions cheaper than rcp_fast.
+__device__ __forceinline__ double rcp_cell(double a) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(a));
+    return fma(r, fma(-a, r, 1.0), r);
+}
+
 // log2(t) for positive normal t.  log2(t) = e + (2/ln2) * atanh(s) with m = t * 2^-e in
 // [sqrt(1/2), sqrt(2)), s = (m-1)/(m+1).  Max relative error ~4e-16.
 __device__ __forceinline__ double log2_fast(double t) {
