@@ -159,6 +159,7 @@ int launch_solve(cvar_plan* p, const double* d_day, int64_t T, const AlphaSet& A
     case KV: solve_kernel<KV><<<grid, block, p->smem_bytes, st>>>(p->kp, d_day, (long long)T, A, order, d_traj, d_mass, d_cells); break;
     switch (p->kernel_variant) {
         CVAR_LAUNCH_SOLVE(0) CVAR_LAUNCH_SOLVE(1) CVAR_LAUNCH_SOLVE(2) CVAR_LAUNCH_SOLVE(3) CVAR_LAUNCH_SOLVE(4) CVAR_LAUNCH_SOLVE(5)
+        CVAR_LAUNCH_SOLVE(6)
         default: return CVAR_ERR_COPULA;
     }
 #undef CVAR_LAUNCH_SOLVE
@@ -173,6 +174,7 @@ int launch_strip(cvar_plan* p, const double* d_day, int64_t T, const double* d_b
     case KV: strip_mass_kernel<KV><<<grid, block, p->smem_bytes, st>>>(p->kp, d_day, d_bounds, d_out, d_cells); break;
     switch (p->kernel_variant) {
         CVAR_LAUNCH_STRIP(0) CVAR_LAUNCH_STRIP(1) CVAR_LAUNCH_STRIP(2) CVAR_LAUNCH_STRIP(3) CVAR_LAUNCH_STRIP(4) CVAR_LAUNCH_STRIP(5)
+        CVAR_LAUNCH_STRIP(6)
         default: return CVAR_ERR_COPULA;
     }
 #undef CVAR_LAUNCH_STRIP
@@ -296,7 +298,8 @@ int cvar_plan_create(const cvar_desc_t* desc, const double* x, const double* dx,
     if (rc) { delete p; return rc; }
     p->sm_count = prop.multiProcessorCount;
     // kernel variant: Student-t cells use the table-assisted power when its binomial series converges fast enough
-    // for this nu (degree <= 13 for a truncation error below 1e-17), else the generic log2/exp2 cell
+    // for this nu (degree <= 13 for a relative truncation error below 2e-15, against a cell budget of 1e-13), else
+    // the generic log2/exp2 cell
     p->kernel_variant = desc->copula;
     double powc[POW_MAX_DEG + 2] = {0};
     if (desc->copula == CVAR_COPULA_STUDENT && !std::getenv("CVAR_STUDENT_GENERIC")) {
@@ -307,9 +310,10 @@ int cvar_plan_create(const cvar_desc_t* desc, const double* x, const double* dx,
         for (int k = 1; k <= POW_MAX_DEG + 1; ++k) {
             powc[k] = powc[k - 1] * (-(c + k - 1)) / k;   // binom(-c, k)
             pw *= fmax_;
-            if (need < 0 && std::fabs(powc[k]) * pw < 1e-17) need = k - 1;   // first neglected term is small enough
+            if (need < 0 && std::fabs(powc[k]) * pw < 2e-15) need = k - 1;   // first neglected term is small enough
         }
-        if (need >= 0 && need <= 7) p->kernel_variant = KV_STUDENT_POW7;
+        if (need >= 0 && need <= 6) p->kernel_variant = KV_STUDENT_POW6;
+        else if (need >= 0 && need <= 8) p->kernel_variant = KV_STUDENT_POW8;
         else if (need >= 0 && need <= 10) p->kernel_variant = KV_STUDENT_POW10;
         else if (need >= 0 && need <= 13) p->kernel_variant = KV_STUDENT_POW13;
     }
@@ -463,7 +467,7 @@ int cvar_plan_create(const cvar_desc_t* desc, const double* x, const double* dx,
         }                                                                                                          \
         break;
     switch (p->kernel_variant) {
-        CVAR_PREP(0) CVAR_PREP(1) CVAR_PREP(2) CVAR_PREP(3) CVAR_PREP(4) CVAR_PREP(5)
+        CVAR_PREP(0) CVAR_PREP(1) CVAR_PREP(2) CVAR_PREP(3) CVAR_PREP(4) CVAR_PREP(5) CVAR_PREP(6)
         default: break;
     }
 #undef CVAR_PREP

@@ -26,10 +26,11 @@ constexpr int CTA_THREADS_LARGE = 512;
 constexpr int MAX_CTA_WARPS = CTA_THREADS_LARGE / 32;
 // Kernel variants (template parameter COPULA of the kernels below): the three copula families plus three
 // Student-t variants whose cell uses the table-assisted power with a binomial series of fixed degree.
-constexpr int KV_GAUSSIAN = 0, KV_STUDENT = 1, KV_PLACKETT = 2, KV_STUDENT_POW7 = 3, KV_STUDENT_POW10 = 4, KV_STUDENT_POW13 = 5;
-__host__ __device__ constexpr bool kv_is_student(int kv) { return kv == KV_STUDENT || kv >= KV_STUDENT_POW7; }
+constexpr int KV_GAUSSIAN = 0, KV_STUDENT = 1, KV_PLACKETT = 2, KV_STUDENT_POW6 = 3, KV_STUDENT_POW8 = 4, KV_STUDENT_POW10 = 5,
+              KV_STUDENT_POW13 = 6, KV_COUNT = 7;
+__host__ __device__ constexpr bool kv_is_student(int kv) { return kv == KV_STUDENT || kv >= KV_STUDENT_POW6; }
 __host__ __device__ constexpr int kv_pow_degree(int kv) {
-    return kv == KV_STUDENT_POW7 ? 7 : kv == KV_STUDENT_POW10 ? 10 : kv == KV_STUDENT_POW13 ? 13 : 0;
+    return kv == KV_STUDENT_POW6 ? 6 : kv == KV_STUDENT_POW8 ? 8 : kv == KV_STUDENT_POW10 ? 10 : kv == KV_STUDENT_POW13 ? 13 : 0;
 }
 
 // independent cells per thread per loop trip (FP64 latency hiding); the cheap cells need more of them
@@ -340,7 +341,8 @@ struct RowStudentPow {  // Student-t: W = rowfac * A1[j] * ( c0 + (y1'[j] - m0)^
         return b * pow_neg_c<DEG>(t, P.powc, S.ptab);
     }
 };
-template <> struct Row<KV_STUDENT_POW7> : RowStudentPow<7> {};
+template <> struct Row<KV_STUDENT_POW6> : RowStudentPow<6> {};
+template <> struct Row<KV_STUDENT_POW8> : RowStudentPow<8> {};
 template <> struct Row<KV_STUDENT_POW10> : RowStudentPow<10> {};
 template <> struct Row<KV_STUDENT_POW13> : RowStudentPow<13> {};
 

@@ -126,8 +126,8 @@ typedef struct cvar_plan_info {
     double tq_table_max_rel_err; /* Student only: measured max of |table - iterative| / max(|iterative|, 0.1)
                                     over 4 off-node probes per table interval; 0 otherwise */
     double last_kernel_ms;     /* device time of the last *_host solve (CUDA events), ms */
-    int32_t kernel_variant;    /* 0 Gaussian, 1 Student-t (generic log2/exp2 cell), 2 Plackett, 3/4/5 Student-t with the
-                                  table-assisted power cell of degree 7/10/13 (picked from nu at plan creation) */
+    int32_t kernel_variant;    /* 0 Gaussian, 1 Student-t (generic log2/exp2 cell), 2 Plackett, 3/4/5/6 Student-t with the
+                                  table-assisted power cell of degree 6/8/10/13 (picked from nu at plan creation) */
     int32_t reserved;
 } cvar_plan_info_t;
 
