@@ -421,11 +421,12 @@ int cvar_plan_create(const cvar_desc_t* desc, const double* x, const double* dx,
         PLAN_TRY(cudaMalloc(&d_err, sizeof(unsigned long long)));
         PLAN_TRY(cudaMemsetAsync(d_err, 0, sizeof(unsigned long long), p->stream));
         tq_table_check_kernel<<<TQ_INTERVALS, 32, 0, p->stream>>>(desc->nu, p->d_tq_table, kp.tq_tail_lc, d_err);
-        PLAN_TRY(cudaGetLastError());
+        cudaError_t ce = cudaGetLastError();
         unsigned long long bits = 0;
-        PLAN_TRY(cudaMemcpyAsync(&bits, d_err, sizeof(bits), cudaMemcpyDeviceToHost, p->stream));
-        PLAN_TRY(cudaStreamSynchronize(p->stream));
+        if (ce == cudaSuccess) ce = cudaMemcpyAsync(&bits, d_err, sizeof(bits), cudaMemcpyDeviceToHost, p->stream);
+        if (ce == cudaSuccess) ce = cudaStreamSynchronize(p->stream);
         cudaFree(d_err);
+        PLAN_TRY(ce);
         std::memcpy(&p->tq_err, &bits, sizeof(double));
         kp.tq_table = p->d_tq_table;
         // table-assisted log2 of the cell loop: constants scaled by -(nu+2)/2
@@ -444,7 +445,6 @@ int cvar_plan_create(const cvar_desc_t* desc, const double* x, const double* dx,
     }
     PLAN_TRY(cudaStreamSynchronize(p->stream));
 
-    // opt in to the dynamic shared memory this grid needs, for every instantiation
     // opt in to the dynamic shared memory this grid needs (for the instantiation this plan uses) and size the CTAs.
     // CTA size (measured on B200, tools/sweep_cta_threads.sh): registers cap an SM at 16 resident warps whatever the
     // CTA size, so small grids do best with small CTAs (cheaper barriers, more days in flight): 64 threads for
@@ -860,6 +860,23 @@ int cvar_msm_forecast_host(int32_t k, int32_t n_assets, const double* stay_prob,
     return rc;
 }
 
+int cvar_kalman_forecast_device(int32_t n_assets, const double* a, const double* l, const double* q, double ukf_alpha,
+                                double ukf_beta, double ukf_kappa, const double* returns, int64_t T, int64_t N,
+                                int64_t window_stride, double* sigma_out, int32_t* status, void* stream) {
+    if (!a || !l || !q || !returns || !sigma_out || !status) return CVAR_ERR_NULL;
+    if (n_assets < 1 || T < 0 || N < 1 || window_stride < 1) return CVAR_ERR_SIZE;
+    if (T == 0) return CVAR_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t L = (T - 1) * window_stride + N;
+    for (int k = 0; k < n_assets; ++k) {
+        KalmanAsset K{a[k], l[k], q[k], ukf_alpha, ukf_beta, ukf_kappa};
+        kalman_forecast_kernel<<<(unsigned)((T + 127) / 128), 128, 0, st>>>(K, returns + k * L, (long long)T, (int)N,
+                                                                           (long long)window_stride, sigma_out + k,
+                                                                           (long long)n_assets, status);
+    }
+    return (int)cudaGetLastError();
+}
+
 int cvar_kalman_forecast_host(int32_t n_assets, const double* a, const double* l, const double* q, double ukf_alpha,
                               double ukf_beta, double ukf_kappa, const double* returns, int64_t T, int64_t N,
                               int64_t window_stride, double* sigma_out, int32_t* status_out, double* kernel_ms_out, int device) {
@@ -870,83 +887,97 @@ int cvar_kalman_forecast_host(int32_t n_assets, const double* a, const double* l
     if (T == 0) return CVAR_OK;
     DeviceGuard guard(device);
     const int64_t L = (T - 1) * window_stride + N;
-    double *d_ret = nullptr, *d_out = nullptr;
-    int* d_st = nullptr;
-    CU_TRY(cudaMalloc(&d_ret, sizeof(double) * n_assets * L));
-    cudaError_t e = cudaMalloc(&d_out, sizeof(double) * T * n_assets);
-    if (e == cudaSuccess) e = cudaMalloc(&d_st, sizeof(int));
-    if (e != cudaSuccess) { cudaFree(d_ret); cudaFree(d_out); return (int)e; }
+    const size_t b_ret = align256(sizeof(double) * n_assets * L), b_out = align256(sizeof(double) * T * n_assets);
+    char* base = nullptr;
+    CU_TRY(cudaMalloc(&base, b_ret + b_out + 256));
+    double* d_ret = (double*)base;
+    double* d_out = (double*)(base + b_ret);
+    int* d_st = (int*)(base + b_ret + b_out);
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0);
     cudaEventCreate(&e1);
-    e = cudaMemcpy(d_ret, returns, sizeof(double) * n_assets * L, cudaMemcpyHostToDevice);
+    cudaError_t e = cudaMemcpy(d_ret, returns, sizeof(double) * n_assets * L, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemset(d_st, 0, sizeof(int));
-    if (e == cudaSuccess) {
+    int rc = (int)e;
+    if (!rc) {
         cudaEventRecord(e0);
-        for (int k = 0; k < n_assets; ++k) {
-            KalmanAsset K{a[k], l[k], q[k], ukf_alpha, ukf_beta, ukf_kappa};
-            kalman_forecast_kernel<<<(unsigned)((T + 127) / 128), 128>>>(K, d_ret + k * L, (long long)T, (int)N,
-                                                                        (long long)window_stride, d_out + k, (long long)n_assets, d_st);
-        }
+        rc = cvar_kalman_forecast_device(n_assets, a, l, q, ukf_alpha, ukf_beta, ukf_kappa, d_ret, T, N, window_stride, d_out,
+                                         d_st, nullptr);
         cudaEventRecord(e1);
-        e = cudaGetLastError();
     }
-    if (e == cudaSuccess) e = cudaMemcpy(sigma_out, d_out, sizeof(double) * T * n_assets, cudaMemcpyDeviceToHost);
+    if (!rc) rc = (int)cudaMemcpy(sigma_out, d_out, sizeof(double) * T * n_assets, cudaMemcpyDeviceToHost);
     int st = 0;
-    if (e == cudaSuccess) e = cudaMemcpy(&st, d_st, sizeof(int), cudaMemcpyDeviceToHost);
+    if (!rc) rc = (int)cudaMemcpy(&st, d_st, sizeof(int), cudaMemcpyDeviceToHost);
     if (status_out) *status_out = st;
     float ms = 0.f;
-    if (e == cudaSuccess && kernel_ms_out && cudaEventElapsedTime(&ms, e0, e1) == cudaSuccess) *kernel_ms_out = ms;
+    if (!rc && kernel_ms_out && cudaEventElapsedTime(&ms, e0, e1) == cudaSuccess) *kernel_ms_out = ms;
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
-    cudaFree(d_ret);
-    cudaFree(d_out);
-    cudaFree(d_st);
-    return (int)e;
+    cudaFree(base);
+    return rc;
+}
+
+static int check_garch(int32_t n_assets, const double* omega, const int32_t* p, const int32_t* q, const double* alpha,
+                       const double* beta, const double* returns, int64_t T, int64_t N, int64_t window_stride,
+                       const double* sigma_out) {
+    if (!omega || !p || !q || !alpha || !beta || !returns || !sigma_out) return CVAR_ERR_NULL;
+    if (n_assets < 1 || T < 0 || N < 1 || window_stride < 1) return CVAR_ERR_SIZE;
+    for (int a = 0; a < n_assets; ++a)
+        if (p[a] < 1 || q[a] < 1 || p[a] > GARCH_MAX_ORDER || q[a] > GARCH_MAX_ORDER || p[a] > N || q[a] > N) return CVAR_ERR_PARAM;
+    return CVAR_OK;
+}
+
+int cvar_garch_forecast_device(int32_t n_assets, const double* omega, const int32_t* p, const int32_t* q, const double* alpha,
+                               const double* beta, const double* returns, int64_t T, int64_t N, int64_t window_stride,
+                               double* sigma_out, void* stream) {
+    int rc = check_garch(n_assets, omega, p, q, alpha, beta, returns, T, N, window_stride, sigma_out);
+    if (rc || T == 0) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t L = (T - 1) * window_stride + N;
+    for (int a = 0; a < n_assets; ++a) {
+        GarchAsset G;
+        std::memset(&G, 0, sizeof(G));
+        G.omega = omega[a]; G.p = p[a]; G.q = q[a];
+        for (int i = 0; i < p[a]; ++i) G.alpha[i] = alpha[a * GARCH_MAX_ORDER + i];
+        for (int j = 0; j < q[a]; ++j) G.beta[j] = beta[a * GARCH_MAX_ORDER + j];
+        garch_forecast_kernel<<<(unsigned)((T + 127) / 128), 128, 0, st>>>(G, returns + a * L, (long long)T, (int)N,
+                                                                          (long long)window_stride, sigma_out + a,
+                                                                          (long long)n_assets);
+    }
+    return (int)cudaGetLastError();
 }
 
 int cvar_garch_forecast_host(int32_t n_assets, const double* omega, const int32_t* p, const int32_t* q, const double* alpha,
                              const double* beta, const double* returns, int64_t T, int64_t N, int64_t window_stride,
                              double* sigma_out, double* kernel_ms_out, int device) {
-    if (!omega || !p || !q || !alpha || !beta || !returns || !sigma_out) return CVAR_ERR_NULL;
-    if (n_assets < 1 || T < 0 || N < 1 || window_stride < 1) return CVAR_ERR_SIZE;
-    for (int a = 0; a < n_assets; ++a)
-        if (p[a] < 1 || q[a] < 1 || p[a] > GARCH_MAX_ORDER || q[a] > GARCH_MAX_ORDER || p[a] > N || q[a] > N) return CVAR_ERR_PARAM;
+    int rc = check_garch(n_assets, omega, p, q, alpha, beta, returns, T, N, window_stride, sigma_out);
+    if (rc) return rc;
     device = pick_device(device);
     if (device < 0) return CVAR_ERR_NO_DEVICE;
     if (T == 0) return CVAR_OK;
     DeviceGuard guard(device);
     const int64_t L = (T - 1) * window_stride + N;
-    double *d_ret = nullptr, *d_out = nullptr;
-    CU_TRY(cudaMalloc(&d_ret, sizeof(double) * n_assets * L));
-    cudaError_t e = cudaMalloc(&d_out, sizeof(double) * T * n_assets);
-    if (e != cudaSuccess) { cudaFree(d_ret); return (int)e; }
+    const size_t b_ret = align256(sizeof(double) * n_assets * L);
+    char* base = nullptr;
+    CU_TRY(cudaMalloc(&base, b_ret + sizeof(double) * T * n_assets));
+    double* d_ret = (double*)base;
+    double* d_out = (double*)(base + b_ret);
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0);
     cudaEventCreate(&e1);
-    e = cudaMemcpy(d_ret, returns, sizeof(double) * n_assets * L, cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) {
+    rc = (int)cudaMemcpy(d_ret, returns, sizeof(double) * n_assets * L, cudaMemcpyHostToDevice);
+    if (!rc) {
         cudaEventRecord(e0);
-        for (int a = 0; a < n_assets; ++a) {
-            GarchAsset G;
-            std::memset(&G, 0, sizeof(G));
-            G.omega = omega[a]; G.p = p[a]; G.q = q[a];
-            for (int i = 0; i < p[a]; ++i) G.alpha[i] = alpha[a * GARCH_MAX_ORDER + i];
-            for (int j = 0; j < q[a]; ++j) G.beta[j] = beta[a * GARCH_MAX_ORDER + j];
-            garch_forecast_kernel<<<(unsigned)((T + 127) / 128), 128>>>(G, d_ret + a * L, (long long)T, (int)N,
-                                                                       (long long)window_stride, d_out + a, (long long)n_assets);
-        }
+        rc = cvar_garch_forecast_device(n_assets, omega, p, q, alpha, beta, d_ret, T, N, window_stride, d_out, nullptr);
         cudaEventRecord(e1);
-        e = cudaGetLastError();
     }
-    if (e == cudaSuccess) e = cudaMemcpy(sigma_out, d_out, sizeof(double) * T * n_assets, cudaMemcpyDeviceToHost);
+    if (!rc) rc = (int)cudaMemcpy(sigma_out, d_out, sizeof(double) * T * n_assets, cudaMemcpyDeviceToHost);
     float ms = 0.f;
-    if (e == cudaSuccess && kernel_ms_out && cudaEventElapsedTime(&ms, e0, e1) == cudaSuccess) *kernel_ms_out = ms;
+    if (!rc && kernel_ms_out && cudaEventElapsedTime(&ms, e0, e1) == cudaSuccess) *kernel_ms_out = ms;
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
-    cudaFree(d_ret);
-    cudaFree(d_out);
-    return (int)e;
+    cudaFree(base);
+    return rc;
 }
 
 }  // extern "C"

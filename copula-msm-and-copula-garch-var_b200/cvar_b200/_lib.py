@@ -65,6 +65,10 @@ _PROTOTYPES = {
                                             C.c_int64, C.c_int64, C.c_void_p, C.POINTER(C.c_double), C.c_int]),
     "cvar_kalman_forecast_host": (C.c_int, [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_void_p,
                                              C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_double), C.c_int]),
+    "cvar_garch_forecast_device": (C.c_int, [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
+                                              C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
+    "cvar_kalman_forecast_device": (C.c_int, [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_double,
+                                               C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "cvar_fp64_peak_host": (C.c_int, [C.c_int, C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "cvar_copula_density_host": (C.c_int, [C.c_int32, C.c_double, C.c_double, C.c_double, C.c_void_p, C.c_int64, C.c_void_p, C.c_int]),
 }

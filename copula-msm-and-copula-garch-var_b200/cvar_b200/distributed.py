@@ -53,3 +53,51 @@ def solve_sharded(plan, day_params_local: torch.Tensor, T_total: int, alphas, pt
     traj = gather_trajectories(traj_local, T_total, group) if dist.is_initialized() and dist.get_world_size(group) > 1 \
         else traj_local
     return plan.finalize_device(traj, ptf_mean=ptf_mean)
+
+
+def window_slice(T: int, N: int, world_size: int, rank: int, window_stride: int = 1) -> tuple[int, int, int, int]:
+    """(day_start, day_stop, ret_start, ret_stop): the rolling windows [day_start, day_stop) of `rank` read the
+    returns [ret_start, ret_stop) of the (T-1)*window_stride + N long series (ret_stop == ret_start for an empty
+    block).  Neighbouring ranks overlap by N - window_stride returns, the price of filtering without a halo
+    exchange: 8.6 KB per asset at N = 1135 against a 1.6 ms filter."""
+    d0, d1 = shard_bounds(T, world_size, rank)
+    if d1 <= d0:
+        return d0, d1, 0, 0
+    return d0, d1, d0 * window_stride, (d1 - 1) * window_stride + N
+
+
+def var_from_returns_sharded(plan, producer, returns, N: int, alphas, ptf_mean: float = 0.0, window_stride: int = 1,
+                             group=None):
+    """Returns -> forecasts -> VaR with nothing but the return series crossing PCIe.
+
+    returns  : (n_assets, L) centred returns on the HOST (numpy or a pinned CPU tensor), L = (T-1)*window_stride + N,
+               identical on every rank; each rank uploads only the slice its windows read
+    producer : callable(cuda tensor (n_assets, L_local)) -> day_params CUDA tensor (T_local, 2[, q]) -- e.g.
+               ``lambda r: msm_forecast_device(r, params, k, N)[0]`` or ``lambda r: garch_forecast_device(r, ..., N)``
+    -> (var[n_alpha, T], case[n_alpha, T], iterations[n_alpha]) CUDA tensors, the same on every rank and for any
+       number of ranks (the forecast of a window depends on its own returns only; the solve's single cross-day
+       coupling is resolved by `solve_sharded`).
+    """
+    import numpy as np
+
+    r = returns if isinstance(returns, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(returns, dtype=np.float64))
+    if r.dim() != 2 or r.dtype != torch.float64:
+        raise ValueError("returns must be a float64 (n_assets, L) array")
+    L = r.shape[1]
+    if L < N or (L - N) % window_stride:
+        raise ValueError("series length does not match (T-1)*window_stride + N")
+    T = (L - N) // window_stride + 1
+    sharded = dist.is_initialized() and dist.get_world_size(group) > 1
+    world, rank = (dist.get_world_size(group), dist.get_rank(group)) if sharded else (1, 0)
+    d0, d1, r0, r1 = window_slice(T, N, world, rank, window_stride)
+    dev = torch.device("cuda", plan.device)
+    with torch.cuda.device(dev):
+        if d1 > d0:
+            local = r[:, r0:r1].contiguous().to(dev, non_blocking=True)
+            day = producer(local)
+        else:
+            shape = (0, 2) if plan.marginal == "single" else (0, 2, plan.q)
+            day = torch.empty(shape, dtype=torch.float64, device=dev)
+        if day.shape[0] != d1 - d0:
+            raise ValueError(f"producer returned {day.shape[0]} days for a block of {d1 - d0} windows")
+        return solve_sharded(plan, day.contiguous(), T, alphas, ptf_mean=ptf_mean, group=group)

@@ -73,13 +73,7 @@ def msm_forecast(returns, params, k: int, N: int, *, window_stride: int = 1, ret
     return (*res, sp, info) if return_state_probs else (*res, info)
 
 
-def garch_forecast(returns, omega, alpha_vects, beta_vects, N: int, *, window_stride: int = 1, device: int = -1):
-    """One-step GARCH(p,q) volatility forecast at the end of every rolling window: sigma (T, n_assets)."""
-    r = np.ascontiguousarray(np.atleast_2d(returns), dtype=np.float64)
-    na, L = r.shape
-    if (L - N) % window_stride or L < N:
-        raise ValueError("series length does not match (T-1)*window_stride + N")
-    T = (L - N) // window_stride + 1
+def _garch_pack(na, omega, alpha_vects, beta_vects):
     om = np.ascontiguousarray(np.broadcast_to(np.asarray(omega, dtype=np.float64), (na,)))
     al, be = np.zeros((na, 8)), np.zeros((na, 8))
     p, q = np.empty(na, np.int32), np.empty(na, np.int32)
@@ -89,6 +83,17 @@ def garch_forecast(returns, omega, alpha_vects, beta_vects, N: int, *, window_st
             raise ValueError("GARCH parameters must be positive with sum(alpha) + sum(beta) < 1")   # garch/estimation.py:22-38
         p[a], q[a] = len(av), len(bv)
         al[a, :len(av)], be[a, :len(bv)] = av, bv
+    return om, p, q, al, be
+
+
+def garch_forecast(returns, omega, alpha_vects, beta_vects, N: int, *, window_stride: int = 1, device: int = -1):
+    """One-step GARCH(p,q) volatility forecast at the end of every rolling window: sigma (T, n_assets)."""
+    r = np.ascontiguousarray(np.atleast_2d(returns), dtype=np.float64)
+    na, L = r.shape
+    if (L - N) % window_stride or L < N:
+        raise ValueError("series length does not match (T-1)*window_stride + N")
+    T = (L - N) // window_stride + 1
+    om, p, q, al, be = _garch_pack(na, omega, alpha_vects, beta_vects)
     out = np.empty((T, na))
     ms = C.c_double(0.0)
     st = _lib.load().cvar_garch_forecast_host(na, _ptr(om), _ptr(p), _ptr(q), _ptr(al), _ptr(be), _ptr(r), T, N, window_stride,
@@ -147,3 +152,47 @@ def msm_forecast_device(returns, params, k: int, N: int, *, window_stride: int =
                                                   C.c_void_p(stream))
     _lib.check(st, "cvar_msm_forecast_device")
     return out, np.array(sig), status
+
+
+def _device_series(returns, N, window_stride):
+    import torch
+
+    if not (isinstance(returns, torch.Tensor) and returns.is_cuda and returns.dtype == torch.float64 and returns.is_contiguous()
+            and returns.dim() == 2):
+        raise ValueError("returns must be a contiguous CUDA float64 tensor of shape (n_assets, L)")
+    na, L = returns.shape
+    if (L - N) % window_stride or L < N:
+        raise ValueError("series length does not match (T-1)*window_stride + N")
+    return na, (L - N) // window_stride + 1
+
+
+def garch_forecast_device(returns, omega, alpha_vects, beta_vects, N: int, *, window_stride: int = 1):
+    """Device-resident `garch_forecast`: CUDA tensor in, sigma (T, n_assets) CUDA tensor out, on torch's current stream."""
+    import torch
+
+    na, T = _device_series(returns, N, window_stride)
+    om, p, q, al, be = _garch_pack(na, omega, alpha_vects, beta_vects)
+    out = torch.empty((T, na), dtype=torch.float64, device=returns.device)
+    stream = torch.cuda.current_stream(returns.device).cuda_stream
+    with torch.cuda.device(returns.device):
+        st = _lib.load().cvar_garch_forecast_device(na, _ptr(om), _ptr(p), _ptr(q), _ptr(al), _ptr(be), C.c_void_p(returns.data_ptr()),
+                                                    T, N, window_stride, C.c_void_p(out.data_ptr()), C.c_void_p(stream))
+    _lib.check(st, "cvar_garch_forecast_device")
+    return out
+
+
+def kalman_forecast_device(returns, a, l, q, N: int, *, window_stride: int = 1, ukf=(1.6, 2.0, 1.75)):
+    """Device-resident `kalman_forecast`: -> sigma (T, n_assets) CUDA tensor, status (cuda int32, 1 = a window failed)."""
+    import torch
+
+    na, T = _device_series(returns, N, window_stride)
+    av, lv, qv = (np.ascontiguousarray(np.broadcast_to(np.asarray(v, dtype=np.float64), (na,))) for v in (a, l, q))
+    out = torch.empty((T, na), dtype=torch.float64, device=returns.device)
+    status = torch.zeros((1,), dtype=torch.int32, device=returns.device)
+    stream = torch.cuda.current_stream(returns.device).cuda_stream
+    with torch.cuda.device(returns.device):
+        st = _lib.load().cvar_kalman_forecast_device(na, _ptr(av), _ptr(lv), _ptr(qv), float(ukf[0]), float(ukf[1]), float(ukf[2]),
+                                                     C.c_void_p(returns.data_ptr()), T, N, window_stride,
+                                                     C.c_void_p(out.data_ptr()), C.c_void_p(status.data_ptr()), C.c_void_p(stream))
+    _lib.check(st, "cvar_kalman_forecast_device")
+    return out, status

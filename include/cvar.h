@@ -266,10 +266,15 @@ int cvar_msm_forecast_device(int32_t k, int32_t n_assets, const double* stay_pro
  * calc_forecast (utils/model_estimation/model/garch_estimation.py:190-231, garch/forecast.py:5-18,
  * garch/estimation.py:40-65).  alpha / beta are [n_assets][8] (unused entries ignored), p, q <= 8.
  *   sigma_out [T][n_assets] == the solve's day_params for CVAR_MARGINAL_SINGLE with n_assets = 2
+ * _device: returns and sigma_out are DEVICE pointers, the model parameters stay host pointers; enqueues on `stream`,
+ *          so the forecast can feed cvar_solve_device on the same stream without a host round trip.
  */
 int cvar_garch_forecast_host(int32_t n_assets, const double* omega, const int32_t* p, const int32_t* q, const double* alpha,
                              const double* beta, const double* returns, int64_t T, int64_t N, int64_t window_stride,
                              double* sigma_out, double* kernel_ms_out, int device);
+int cvar_garch_forecast_device(int32_t n_assets, const double* omega, const int32_t* p, const int32_t* q, const double* alpha,
+                               const double* beta, const double* returns, int64_t T, int64_t N, int64_t window_stride,
+                               double* sigma_out, void* stream);
 
 /*
  * Kalman mean-reverting log-volatility model: exp(last predicted state mean) of the scalar unscented filter per
@@ -279,10 +284,14 @@ int cvar_garch_forecast_host(int32_t n_assets, const double* omega, const int32_
  * in the reference.  status 1 = the filter's normalising constant collapsed in some window (the reference returns
  * an error tuple there); that window's forecast is NaN.
  *   sigma_out [T][n_assets]
+ * _device: returns, sigma_out and status (one int32, zeroed by the caller) are DEVICE pointers; enqueues on `stream`.
  */
 int cvar_kalman_forecast_host(int32_t n_assets, const double* a, const double* l, const double* q, double ukf_alpha,
                               double ukf_beta, double ukf_kappa, const double* returns, int64_t T, int64_t N,
                               int64_t window_stride, double* sigma_out, int32_t* status_out, double* kernel_ms_out, int device);
+int cvar_kalman_forecast_device(int32_t n_assets, const double* a, const double* l, const double* q, double ukf_alpha,
+                                double ukf_beta, double ukf_kappa, const double* returns, int64_t T, int64_t N,
+                                int64_t window_stride, double* sigma_out, int32_t* status, void* stream);
 
 #ifdef __cplusplus
 }

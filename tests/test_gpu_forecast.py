@@ -164,3 +164,54 @@ def test_device_resident_forecast_feeds_the_solve_without_host_round_trip(fc, cu
     assert int(status.item()) == 0 and np.array_equal(sig, host_sig)
     assert np.array_equal(d_pbs.cpu().numpy(), host_pbs)
     assert np.array_equal(var.cpu().numpy(), want.var)
+
+
+def test_device_resident_garch_and_kalman_equal_their_host_entry_points(fc, cuda_device):
+    import torch
+    rng = np.random.default_rng(77)
+    N, T = 60, 37
+    series = rng.standard_normal((2, T + N - 1)) * np.array([[0.9], [1.3]])
+    d_series = torch.from_numpy(series).to(cuda_device)
+    g_host, _ = fc.garch_forecast(series, [0.02, 0.03], [[0.09], [0.05, 0.04]], [[0.89], [0.88]], N)
+    g_dev = fc.garch_forecast_device(d_series, [0.02, 0.03], [[0.09], [0.05, 0.04]], [[0.89], [0.88]], N)
+    k_host, info = fc.kalman_forecast(series, [0.97, 0.95], [0.0, 0.1], [0.15, 0.2], N)
+    k_dev, status = fc.kalman_forecast_device(d_series, [0.97, 0.95], [0.0, 0.1], [0.15, 0.2], N)
+    assert g_dev.shape == (T, 2) and np.array_equal(g_dev.cpu().numpy(), g_host)
+    assert np.array_equal(k_dev.cpu().numpy(), k_host) and bool(status.item()) == info["failed"]
+    with pytest.raises(ValueError):
+        fc.garch_forecast_device(torch.from_numpy(series), [0.02, 0.03], [[0.09], [0.05]], [[0.89], [0.88]], N)   # host tensor
+
+
+@pytest.mark.parametrize("family", ["msm", "garch", "kalman"])
+def test_returns_to_var_driver_equals_host_forecast_plus_host_solve(fc, cuda_device, family):
+    """`var_from_returns_sharded` on one rank: upload returns once, forecast and solve on the device."""
+    import torch
+    from cvar_b200 import synthetic as syn
+    from cvar_b200.backend import VarPlan
+    from cvar_b200.distributed import var_from_returns_sharded
+    from cvar_b200.inputs import make_inputs
+    N, T = 80, 11
+    if family == "msm":
+        k = 4
+        prm = [fc.MsmParams(0.4, 1.1, 3.0, 0.3), fc.MsmParams(0.55, 1.4, 5.0, 0.2)]
+        series = np.array([syn.msm_simulate_returns(T + N - 1, k, p.m0, p.sigma_bar, p.b, p.gamma, 70 + i) for i, p in enumerate(prm)])
+        pbs, sig, _ = fc.msm_forecast(series, prm, k, N)
+        inp = make_inputs("student", "mixture", 72, rho=0.5, nu=6.0, probs=pbs, sigma_states=sig)
+        producer = lambda r: fc.msm_forecast_device(r, prm, k, N)[0]
+    else:
+        series = np.random.default_rng(5).standard_normal((2, T + N - 1)) * np.array([[0.8], [1.2]])
+        if family == "garch":
+            args = ([0.02, 0.03], [[0.09], [0.08]], [[0.89], [0.90]])
+            sigma, _ = fc.garch_forecast(series, *args, N)
+            producer = lambda r: fc.garch_forecast_device(r, *args, N)
+        else:
+            args = ([0.97, 0.95], [0.0, 0.1], [0.15, 0.2])
+            sigma, _ = fc.kalman_forecast(series, *args, N)
+            producer = lambda r: fc.kalman_forecast_device(r, *args, N)[0]
+        inp = make_inputs("plackett" if family == "kalman" else "gaussian", "single", 72, rho=0.5, theta=4.2, sigma=sigma)
+    with VarPlan(inp) as plan:
+        want = plan.solve(inp.day_params(), [0.01, 0.05], ptf_mean=0.01)
+        var, case, iters = var_from_returns_sharded(plan, producer, series, N, [0.01, 0.05], ptf_mean=0.01)
+        torch.cuda.synchronize()
+    assert var.cpu().numpy().tobytes() == want.var.tobytes()
+    assert np.array_equal(case.cpu().numpy(), want.case) and np.array_equal(iters.cpu().numpy(), want.iterations)

@@ -64,3 +64,56 @@ def test_two_gpu_sharded_solve_equals_single_gpu(tmp_path):
         got = np.load(os.path.join(tmp_path, f"r{r}.npz"))
         assert got["var"].tobytes() == full.var.tobytes()
         assert np.array_equal(got["case"], full.case) and np.array_equal(got["iters"], full.iterations)
+
+
+def _pipeline_case():
+    from cvar_b200 import synthetic as syn
+    from cvar_b200.forecast import MsmParams
+    k, N, T = 5, 70, 9
+    prm = [MsmParams(0.4, 1.1, 3.0, 0.3), MsmParams(0.55, 1.4, 5.0, 0.2)]
+    series = np.array([syn.msm_simulate_returns(T + N - 1, k, p.m0, p.sigma_bar, p.b, p.gamma, 90 + i) for i, p in enumerate(prm)])
+    return k, N, T, prm, series
+
+
+def _pipeline_worker(rank, world, port, out_dir):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        from cvar_b200 import forecast as fc
+        from cvar_b200.backend import VarPlan
+        from cvar_b200.distributed import var_from_returns_sharded
+        from cvar_b200.inputs import make_inputs
+        k, N, T, prm, series = _pipeline_case()
+        _, sig, _ = fc.msm_forecast(series[:, :N], prm, k, N, device=rank)          # vol levels only (run constants)
+        inp = make_inputs("student", "mixture", 96, rho=0.6, nu=5.3, probs=np.full((1, 2, sig.shape[1]), 1.0 / sig.shape[1]),
+                          sigma_states=sig)
+        with VarPlan(inp, device=rank) as plan:
+            var, case, iters = var_from_returns_sharded(plan, lambda r: fc.msm_forecast_device(r, prm, k, N)[0], series, N,
+                                                        [0.01, 0.05])
+            torch.cuda.synchronize()
+            np.savez(os.path.join(out_dir, f"p{rank}.npz"), var=var.cpu().numpy(), case=case.cpu().numpy())
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_gpu_returns_to_var_equals_single_gpu(tmp_path):
+    """Forecast + solve sharded by window block over two GPUs == host forecast + single-GPU solve, bit for bit."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two CUDA devices")
+    import torch.multiprocessing as mp
+    from conftest import PKG_ROOT
+    from cvar_b200 import forecast as fc
+    from cvar_b200.backend import VarPlan
+    from cvar_b200.inputs import make_inputs
+    os.environ["PYTHONPATH"] = f"{PKG_ROOT}:{os.path.dirname(__file__)}:{os.environ.get('PYTHONPATH', '')}"
+    k, N, T, prm, series = _pipeline_case()
+    pbs, sig, _ = fc.msm_forecast(series, prm, k, N, device=0)
+    inp = make_inputs("student", "mixture", 96, rho=0.6, nu=5.3, probs=pbs, sigma_states=sig)
+    with VarPlan(inp, device=0) as plan:
+        full = plan.solve(inp.day_params(), [0.01, 0.05])
+    mp.spawn(_pipeline_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    for r in range(2):
+        got = np.load(os.path.join(tmp_path, f"p{r}.npz"))
+        assert got["var"].tobytes() == full.var.tobytes() and np.array_equal(got["case"], full.case)

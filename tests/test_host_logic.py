@@ -166,3 +166,23 @@ def test_work_model_matches_survey_figures():
     c = 0.382 * 2048 ** 2
     assert abs(wm.algorithmic_flops("student", "single", 1, 2048, [c]) - 1.39e8) < 0.02e8
     assert wm.algorithmic_flops("gaussian", "single", 1, 100, [10, 20]) == 35 * 30 + 2 * 2 * 100 * 262
+
+
+def test_window_slices_cover_the_series_and_match_the_day_shards():
+    """Returns slice of a rank == exactly what its rolling windows read (forecast -> solve chaining)."""
+    from cvar_b200.distributed import shard_bounds, window_slice
+    for T, N, stride, world in [(10, 4, 1, 2), (7, 5, 1, 3), (1000, 1135, 1, 8), (9, 3, 3, 4), (2, 6, 1, 4), (5, 1, 1, 8)]:
+        L = (T - 1) * stride + N
+        seen_days = []
+        for rank in range(world):
+            d0, d1, r0, r1 = window_slice(T, N, world, rank, stride)
+            assert (d0, d1) == shard_bounds(T, world, rank)
+            if d1 == d0:
+                assert r1 == r0
+                continue
+            assert 0 <= r0 < r1 <= L and (r1 - r0 - N) % stride == 0 and (r1 - r0 - N) // stride + 1 == d1 - d0
+            # window w of the full series == window w - d0 of the slice
+            for w in (d0, d1 - 1):
+                assert r0 + (w - d0) * stride == w * stride and w * stride + N <= r1
+            seen_days += list(range(d0, d1))
+        assert seen_days == list(range(T))

@@ -42,3 +42,32 @@ t0 = time.perf_counter(); [fo.garch_forecast_one(0.02, [0.09], [0.89], gser[0][w
 print(json.dumps({"producer": "garch_forecast", "windows": windows, "window_length": N, "kernel_ms": best,
                   "windows_per_s_kernel": windows / (best * 1e-3), "cpu_port_s_per_window": cpu_s,
                   "speedup_vs_one_core": cpu_s * windows / (best * 1e-3)}))
+
+# ---- returns -> VaR on the device (BASELINE configs[2] shape): one upload of the return series, MSM filter, solve,
+# finalize, one download of the VaR vector; timed with CUDA events around the whole chain
+import torch                                                       # noqa: E402
+from cvar_b200.backend import VarPlan                              # noqa: E402
+from cvar_b200.distributed import var_from_returns_sharded         # noqa: E402
+from cvar_b200.inputs import make_inputs                           # noqa: E402
+
+inp = make_inputs("student", "mixture", 2048, rho=0.6, nu=5.3, probs=pbs, sigma_states=sig)
+pinned = torch.from_numpy(series).pin_memory()
+host_var = torch.empty((1, T), dtype=torch.float64).pin_memory()
+with VarPlan(inp) as plan:
+    want = plan.solve(pbs, [0.01])
+    producer = lambda r: fc.msm_forecast_device(r, prm, k, N)[0]   # noqa: E731
+    times = []
+    for it in range(8):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        var, case, iters = var_from_returns_sharded(plan, producer, pinned, N, [0.01])
+        host_var.copy_(var, non_blocking=True)
+        e1.record()
+        torch.cuda.synchronize()
+        times.append(e0.elapsed_time(e1))
+    ms = float(np.median(times[3:]))
+print(json.dumps({"pipeline": "returns -> MSM(k=8) state filter -> Student-copula VaR (c3 shape)", "days": T, "grid": "2048x2048",
+                  "window_length": N, "ms_per_batch_e2e": ms, "days_per_s_e2e": T / (ms * 1e-3),
+                  "h2d_bytes": int(pinned.numel() * 8), "d2h_bytes": int(host_var.numel() * 8),
+                  "bit_identical_to_host_forecast_plus_host_solve": bool(host_var.numpy().tobytes() == want.var.tobytes())}))
