@@ -352,6 +352,9 @@ int cvar_plan_create(const cvar_desc_t* desc, const double* x, const double* dx,
                      std::sqrt(om);
         const double lbeta = std::lgamma(0.5 * nu) + std::lgamma(0.5) - std::lgamma(0.5 * nu + 0.5);
         kp.tq_tail_lc = (-lbeta - 0.5 * std::log(nu)) + 0.5 * (nu - 1.0) * std::log(nu);
+        // t = 1 + y0^2/nu + cs^2 (y1 - rho y0)^2 <= 1 + y_max^2 (1/nu + cs^2 (1+|rho|)^2) must stay below 2^63
+        const double ar = 1.0 + std::fabs(desc->rho);
+        kp.y_max = std::sqrt((std::ldexp(1.0, 63) - 1.0) / (1.0 / nu + cs * cs * ar * ar)) * (1.0 - 1e-9);
     }
     // correlation used by the launch-order proxy only (Plackett: Spearman's rho of the family)
     p->rho_eff = desc->rho;

@@ -69,6 +69,7 @@ struct KernelParams {
     double g_const;      // gaussian: (1-rho^2)^(-1/2)            student: Gamma-ratio / sqrt(1-rho^2)
     double tq_tail_lc;   // student: log of the leading tail coefficient
     double negc;         // student: -(nu+2)/2, the exponent of the quadratic form
+    double y_max;        // student pow variants: clamp of |T_nu^-1(u)| that keeps the quadratic form below 2^63
     double qc[CVAR_LOG2_1P_POLY_DEG + 1];  // student: negc * coefficients of log2(1+f)/f
     const double* logtab;  // student: negc * (-log2 r_i), LOGTAB_SIZE entries (global; staged to shared memory)
     const double* exptab;  // gaussian / student: 2^(i/256), EXPTAB_SIZE entries (global; staged to shared memory)
@@ -102,6 +103,7 @@ struct Smem {
     double* etab;   // [EXPTAB_SIZE] gaussian / student
     double* memo;   // [MEMO_SIZE][4]: (lo, hi, mass, cells) of strips already integrated for an earlier alpha
     double* ptab;   // [POW_MTAB + POW_ETAB] student pow variants (aliases the ltab/etab region)
+    unsigned ptab_s;  // shared-window address of ptab
 };
 
 // doubles of per-variant lookup tables staged in shared memory (after the fixed part)
@@ -139,6 +141,7 @@ __device__ __forceinline__ Smem carve(unsigned char* base, int n, int kv) {
     S.ltab = tables;                                      // KV_STUDENT: ltab then etab
     S.etab = kv == KV_STUDENT ? tables + LOGTAB_SIZE : tables;
     S.ptab = tables;
+    S.ptab_s = (unsigned)__cvta_generic_to_shared(tables);
     return S;
 }
 
@@ -208,6 +211,11 @@ __device__ void stage0(const KernelParams& P, const double* __restrict__ dayp, c
                     y[d] = 0.0;
                     a[d] = 0.0;
                 }
+                // quantiles beyond ~1e9 (u below ~1e-19 even at nu = 2; such u only arise from mixture weights far
+                // below 1e-10) are clamped so that the cell's power table never needs an exponent above 2^63; every
+                // factor of the cell is formed from the clamped value, so the cell stays a density value of the same
+                // tail (it changes by a power of the clamp ratio on a region whose total mass is below 1e-19)
+                if (kv_pow_degree(COPULA) > 0) y[d] = copysign(fmin(fabs(y[d]), P.y_max), y[d]);
             }
             const double l1 = fmax(log2(a[1]), -1100.0);
             if (COPULA == 0) {
@@ -338,7 +346,7 @@ struct RowStudentPow {  // Student-t: W = rowfac * A1[j] * ( c0 + (y1'[j] - m0)^
     __device__ __forceinline__ double cell(const KernelParams& P, const Smem& S, double a, double b) const {
         const double d = a - m0;
         const double t = fma(d, d, c0);  // >= 1
-        return b * pow_neg_c<DEG>(t, P.powc, S.ptab);
+        return b * pow_neg_c<DEG>(t, P.powc, S.ptab_s);
     }
 };
 template <> struct Row<KV_STUDENT_POW6> : RowStudentPow<6> {};

@@ -158,19 +158,33 @@ __global__ void powtab_build_kernel(double c, double* __restrict__ tab) {
     if (i < POW_ETAB) tab[POW_MTAB + i] = exp2(-c * (double)i);
 }
 
+// Requires 1 <= t < 2^POW_ETAB (stage 0 clamps the Student-t quantiles so that this holds, see KernelParams::y_max):
+// the exponent table is indexed without a range check.  Index arithmetic stays "in place": the masked mantissa
+// and exponent fields of t's high word are shifted straight into byte offsets, one integer op each.
+__device__ __forceinline__ double lds_f64(unsigned shared_addr) {
+    double v;
+    asm("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(shared_addr));
+    return v;
+}
+
+// `tab_s` is the shared-window address of the table (cvta.to.shared, hoisted by the caller): with a generic pointer
+// ptxas rebuilds the address from two loop-invariant halves for every lookup
 template <int DEG>
-__device__ __forceinline__ double pow_neg_c(double t, const double* __restrict__ kc, const double* __restrict__ tab) {
-    const int hi = __double2hiint(t);
-    const int e = (hi >> 20) - 1023;
-    const int idx = (hi >> (20 - LOGTAB_BITS)) & (POW_MTAB - 1);
-    double r = logtab_recip(idx);
-    r = __hiloint2double(__double2hiint(r) - (e << 20), 0);  // r_i * 2^-e
+__device__ __forceinline__ double pow_neg_c(double t, const double* __restrict__ kc, unsigned tab_s) {
+    const unsigned hi = (unsigned)__double2hiint(t);
+    const unsigned mb = hi & (unsigned)((POW_MTAB - 1) << (20 - LOGTAB_BITS));  // interval index, still at bit 13
+    const unsigned eb = hi & 0x7ff00000u;                                       // biased exponent, still at bit 20
+    double r;  // == logtab_recip(idx)
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(__hiloint2double((int)(mb | 0x3ff00000u | (1u << (19 - LOGTAB_BITS))), 0)));
+    r = __hiloint2double(__double2hiint(r) - (int)eb + 0x3ff00000, 0);          // r_i * 2^-e
     const double f = fma(t, r, -1.0);
     double p = kc[DEG];
 #pragma unroll
     for (int k = DEG - 1; k >= 1; --k) p = fma(p, f, kc[k]);
     p = fma(p, f, 1.0);
-    return (tab[idx] * tab[POW_MTAB + min(e, POW_ETAB - 1)]) * p;
+    const double pm = lds_f64(tab_s + (mb >> (20 - LOGTAB_BITS - 3)));
+    const double pe = lds_f64(tab_s + (unsigned)((POW_MTAB - 1023) * 8) + (eb >> 17));
+    return (pm * pe) * p;
 }
 
 // ---------------------------------------------------------------------------------------------
