@@ -101,6 +101,41 @@ int ensure_ws(cvar_plan* p, size_t bytes) {
 
 size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 
+// Near-minimax polynomial of (1+f)^(-c) on |f| <= fm: interpolation at the Chebyshev nodes of degree D, expanded to
+// monomials in f (extended precision, coefficients then rounded to double).  Returns the largest relative error of
+// the ROUNDED polynomial on a dense grid, which is what the plan compares with its budget.
+double fit_pow_series(double c, double fm, int D, double* coef) {
+    const long double PI = 3.141592653589793238462643383279502884L;
+    long double g[POW_MAX_DEG + 1], a[POW_MAX_DEG + 1], mono[POW_MAX_DEG + 1] = {0};
+    long double T[POW_MAX_DEG + 1][POW_MAX_DEG + 1] = {{0}};
+    for (int k = 0; k <= D; ++k) g[k] = powl(1.0L + (long double)fm * cosl(PI * (k + 0.5L) / (D + 1)), -(long double)c);
+    for (int j = 0; j <= D; ++j) {
+        long double acc = 0.0L;
+        for (int k = 0; k <= D; ++k) acc += g[k] * cosl(j * PI * (k + 0.5L) / (D + 1));
+        a[j] = acc * (j == 0 ? 1.0L : 2.0L) / (D + 1);
+    }
+    T[0][0] = 1.0L;
+    if (D >= 1) T[1][1] = 1.0L;
+    for (int j = 2; j <= D; ++j)
+        for (int i = 0; i <= j; ++i) T[j][i] = (i > 0 ? 2.0L * T[j - 1][i - 1] : 0.0L) - T[j - 2][i];
+    for (int j = 0; j <= D; ++j)
+        for (int i = 0; i <= j; ++i) mono[i] += a[j] * T[j][i];
+    long double scale = 1.0L;
+    for (int i = 0; i <= D; ++i) {
+        coef[i] = (double)(mono[i] / scale);
+        scale *= (long double)fm;
+    }
+    long double worst = 0.0L;
+    for (int s = 0; s <= 512; ++s) {
+        const long double f = (long double)fm * (-1.0L + s / 256.0L);
+        long double p = coef[D];
+        for (int i = D - 1; i >= 0; --i) p = p * f + (long double)coef[i];
+        const long double ex = powl(1.0L + f, -(long double)c);
+        worst = std::max(worst, fabsl(p - ex) / ex);
+    }
+    return (double)worst;
+}
+
 __global__ void tq_table_check_kernel(double nu, const double* __restrict__ table, double tail_lc,
                                       unsigned long long* __restrict__ max_err_bits) {
     // off-node probes in every interval: table vs the iterative routine
@@ -297,25 +332,20 @@ int cvar_plan_create(const cvar_desc_t* desc, const double* x, const double* dx,
     int rc = (int)cudaGetDeviceProperties(&prop, device);
     if (rc) { delete p; return rc; }
     p->sm_count = prop.multiProcessorCount;
-    // kernel variant: Student-t cells use the table-assisted power when its binomial series converges fast enough
-    // for this nu (degree <= 13 for a relative truncation error below 2e-15, against a cell budget of 1e-13), else
-    // the generic log2/exp2 cell
+    // kernel variant: Student-t cells use the table-assisted power at the smallest polynomial degree that reproduces
+    // (1+f)^(-(nu+2)/2) to 1e-15 relative on the table's interval (cell budget: 1e-13), else the generic log2/exp2 cell
     p->kernel_variant = desc->copula;
-    double powc[POW_MAX_DEG + 2] = {0};
+    double powc[POW_MAX_DEG + 1] = {0};
     if (desc->copula == CVAR_COPULA_STUDENT && !std::getenv("CVAR_STUDENT_GENERIC")) {
-        const double c = 0.5 * (desc->nu + 2.0), fmax_ = std::ldexp(1.03, -8);
-        powc[0] = 1.0;
-        int need = -1;
-        double pw = 1.0;
-        for (int k = 1; k <= POW_MAX_DEG + 1; ++k) {
-            powc[k] = powc[k - 1] * (-(c + k - 1)) / k;   // binom(-c, k)
-            pw *= fmax_;
-            if (need < 0 && std::fabs(powc[k]) * pw < 2e-15) need = k - 1;   // first neglected term is small enough
+        const int degs[4] = {5, 6, 7, 8}, kvs[4] = {KV_STUDENT_POW5, KV_STUDENT_POW6, KV_STUDENT_POW7, KV_STUDENT_POW8};
+        for (int i = 0; i < 4; ++i) {
+            double trial[POW_MAX_DEG + 1] = {0};
+            if (fit_pow_series(0.5 * (desc->nu + 2.0), POW_FMAX, degs[i], trial) < 1e-15) {
+                std::memcpy(powc, trial, sizeof(powc));
+                p->kernel_variant = kvs[i];
+                break;
+            }
         }
-        if (need >= 0 && need <= 6) p->kernel_variant = KV_STUDENT_POW6;
-        else if (need >= 0 && need <= 8) p->kernel_variant = KV_STUDENT_POW8;
-        else if (need >= 0 && need <= 10) p->kernel_variant = KV_STUDENT_POW10;
-        else if (need >= 0 && need <= 13) p->kernel_variant = KV_STUDENT_POW13;
     }
     p->smem_bytes = smem_bytes_for(n, p->kernel_variant);
     if (p->smem_bytes > (size_t)prop.sharedMemPerBlockOptin) { delete p; return CVAR_ERR_SMEM; }
@@ -435,6 +465,7 @@ int cvar_plan_create(const cvar_desc_t* desc, const double* x, const double* dx,
         // table-assisted log2 of the cell loop: constants scaled by -(nu+2)/2
         constexpr double q1p[] = CVAR_LOG2_1P_POLY;
         kp.negc = -0.5 * (desc->nu + 2.0);
+        kp.inv_nu = 1.0 / desc->nu;
         for (int k = 0; k <= CVAR_LOG2_1P_POLY_DEG; ++k) kp.qc[k] = kp.negc * q1p[k];
         PLAN_TRY(cudaMalloc(&p->d_logtab, sizeof(double) * LOGTAB_SIZE));
         logtab_build_kernel<<<1, LOGTAB_SIZE, 0, p->stream>>>(kp.negc, p->d_logtab);

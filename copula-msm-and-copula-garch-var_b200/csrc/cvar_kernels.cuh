@@ -26,11 +26,11 @@ constexpr int CTA_THREADS_LARGE = 512;
 constexpr int MAX_CTA_WARPS = CTA_THREADS_LARGE / 32;
 // Kernel variants (template parameter COPULA of the kernels below): the three copula families plus three
 // Student-t variants whose cell uses the table-assisted power with a binomial series of fixed degree.
-constexpr int KV_GAUSSIAN = 0, KV_STUDENT = 1, KV_PLACKETT = 2, KV_STUDENT_POW6 = 3, KV_STUDENT_POW8 = 4, KV_STUDENT_POW10 = 5,
-              KV_STUDENT_POW13 = 6, KV_COUNT = 7;
-__host__ __device__ constexpr bool kv_is_student(int kv) { return kv == KV_STUDENT || kv >= KV_STUDENT_POW6; }
+constexpr int KV_GAUSSIAN = 0, KV_STUDENT = 1, KV_PLACKETT = 2, KV_STUDENT_POW5 = 3, KV_STUDENT_POW6 = 4, KV_STUDENT_POW7 = 5,
+              KV_STUDENT_POW8 = 6, KV_COUNT = 7;
+__host__ __device__ constexpr bool kv_is_student(int kv) { return kv == KV_STUDENT || kv >= KV_STUDENT_POW5; }
 __host__ __device__ constexpr int kv_pow_degree(int kv) {
-    return kv == KV_STUDENT_POW6 ? 6 : kv == KV_STUDENT_POW8 ? 8 : kv == KV_STUDENT_POW10 ? 10 : kv == KV_STUDENT_POW13 ? 13 : 0;
+    return kv == KV_STUDENT_POW5 ? 5 : kv == KV_STUDENT_POW6 ? 6 : kv == KV_STUDENT_POW7 ? 7 : kv == KV_STUDENT_POW8 ? 8 : 0;
 }
 
 // independent cells per thread per loop trip (FP64 latency hiding); the cheap cells need more of them
@@ -69,11 +69,12 @@ struct KernelParams {
     double g_const;      // gaussian: (1-rho^2)^(-1/2)            student: Gamma-ratio / sqrt(1-rho^2)
     double tq_tail_lc;   // student: log of the leading tail coefficient
     double negc;         // student: -(nu+2)/2, the exponent of the quadratic form
+    double inv_nu;       // student: 1/nu
     double y_max;        // student pow variants: clamp of |T_nu^-1(u)| that keeps the quadratic form below 2^63
     double qc[CVAR_LOG2_1P_POLY_DEG + 1];  // student: negc * coefficients of log2(1+f)/f
     const double* logtab;  // student: negc * (-log2 r_i), LOGTAB_SIZE entries (global; staged to shared memory)
-    const double* exptab;  // gaussian / student: 2^(i/256), EXPTAB_SIZE entries (global; staged to shared memory)
-    double powc[POW_MAX_DEG + 1];  // student pow variants: binomial coefficients of (1+f)^(-(nu+2)/2)
+    const double* exptab;  // gaussian / student: 2^(i/EXPTAB_SIZE), EXPTAB_SIZE entries (global; staged to shared memory)
+    double powc[POW_MAX_DEG + 1];  // student pow variants: polynomial for (1+f)^(-(nu+2)/2), |f| <= POW_FMAX
     const double* powtab;  // student pow variants: r_i^c (POW_MTAB) then 2^(-c e) (POW_ETAB)
     const double* x;
     const double* dx;
@@ -92,9 +93,8 @@ struct AlphaSet {
 struct Smem {
     double* xs;     // [n] axis (membership searches)
     double2* in;    // [n] inner-axis pair (.x, .y), interleaved so one 16-byte load feeds a cell
-    double* out0;   // [n] outer-axis array 0
-    double* out1;   // [n]
-    double* out2;   // [n]
+    double* out0;   // [n] outer-axis array 0 (gaussian: scaled quantile, student: raw quantile, plackett: u)
+    double* out1;   // [n] outer-axis array 1 (row weight)
     u16* c[3];      // [n] each: inner index bounds per outer row
     double* red;    // [2][MAX_CTA_WARPS]
     unsigned* redc; // [2][MAX_CTA_WARPS]
@@ -116,7 +116,7 @@ __host__ __device__ constexpr int table_doubles(int kv) {
 
 __host__ __device__ inline size_t smem_bytes_for(int n, int kv) {
     size_t npad = (size_t)((n + 3) & ~3);
-    return npad * 8 * 6 + npad * 2 * 3 + 2 * MAX_CTA_WARPS * 8 + 2 * MAX_CTA_WARPS * 4 + 16 + 64 + MEMO_SIZE * 4 * 8 +
+    return npad * 8 * 5 + npad * 2 * 3 + 2 * MAX_CTA_WARPS * 8 + 2 * MAX_CTA_WARPS * 4 + 16 + 64 + MEMO_SIZE * 4 * 8 +
            (size_t)table_doubles(kv) * 8;
 }
 
@@ -128,8 +128,7 @@ __device__ __forceinline__ Smem carve(unsigned char* base, int n, int kv) {
     S.in = reinterpret_cast<double2*>(d + npad);
     S.out0 = d + 3 * npad;
     S.out1 = d + 4 * npad;
-    S.out2 = d + 5 * npad;
-    S.red = d + 6 * npad;
+    S.red = d + 5 * npad;
     u16* h = reinterpret_cast<u16*>(S.red + 2 * MAX_CTA_WARPS);
     S.c[0] = h;
     S.c[1] = h + npad;
@@ -230,9 +229,8 @@ __device__ void stage0(const KernelParams& P, const double* __restrict__ dayp, c
                     S.in[i] = make_double2(P.g_in_scale * y[1], a[1] * exp2(hp * log2(c1)));
                 else
                     S.in[i] = make_double2(P.g_in_scale * y[1], fmax(l1 + hp * log2(c1), -1100.0));
-                S.out0[i] = P.g_out_scale * y[0];
-                S.out1[i] = c0;
-                S.out2[i] = a[0] * P.g_const * exp2(hp * log2(c0));
+                S.out0[i] = y[0];   // the row derives m0 = g_out_scale * y0 and c0 = 1 + y0^2 / nu when it is loaded
+                S.out1[i] = a[0] * P.g_const * exp2(hp * log2(c0));
             }
         }
     }
@@ -323,10 +321,11 @@ struct Row<0> {  // Gaussian:  W = rowfac * 2^( l1[j] - (y1'[j] - m0)^2 )
 template <>
 struct Row<1> {  // Student-t: W = rowfac * 2^( l1[j] - (nu+2)/2 * log2( c0 + (y1'[j] - m0)^2 ) ), table-assisted log2
     double m0, c0, fac;
-    __device__ __forceinline__ void load(const KernelParams&, const Smem& S, int i) {
-        m0 = S.out0[i];
-        c0 = S.out1[i];
-        fac = S.out2[i];
+    __device__ __forceinline__ void load(const KernelParams& P, const Smem& S, int i) {
+        const double y0 = S.out0[i];
+        m0 = P.g_out_scale * y0;
+        c0 = fma(y0 * y0, P.inv_nu, 1.0);
+        fac = S.out1[i];
     }
     __device__ __forceinline__ double cell(const KernelParams& P, const Smem& S, double a, double b) const {
         const double d = a - m0;
@@ -338,10 +337,11 @@ struct Row<1> {  // Student-t: W = rowfac * 2^( l1[j] - (nu+2)/2 * log2( c0 + (y
 template <int DEG>
 struct RowStudentPow {  // Student-t: W = rowfac * A1[j] * ( c0 + (y1'[j] - m0)^2 )^(-(nu+2)/2), table-assisted power
     double m0, c0, fac;
-    __device__ __forceinline__ void load(const KernelParams&, const Smem& S, int i) {
-        m0 = S.out0[i];
-        c0 = S.out1[i];
-        fac = S.out2[i];
+    __device__ __forceinline__ void load(const KernelParams& P, const Smem& S, int i) {
+        const double y0 = S.out0[i];
+        m0 = P.g_out_scale * y0;
+        c0 = fma(y0 * y0, P.inv_nu, 1.0);
+        fac = S.out1[i];
     }
     __device__ __forceinline__ double cell(const KernelParams& P, const Smem& S, double a, double b) const {
         const double d = a - m0;
@@ -349,10 +349,10 @@ struct RowStudentPow {  // Student-t: W = rowfac * A1[j] * ( c0 + (y1'[j] - m0)^
         return b * pow_neg_c<DEG>(t, P.powc, S.ptab_s);
     }
 };
+template <> struct Row<KV_STUDENT_POW5> : RowStudentPow<5> {};
 template <> struct Row<KV_STUDENT_POW6> : RowStudentPow<6> {};
+template <> struct Row<KV_STUDENT_POW7> : RowStudentPow<7> {};
 template <> struct Row<KV_STUDENT_POW8> : RowStudentPow<8> {};
-template <> struct Row<KV_STUDENT_POW10> : RowStudentPow<10> {};
-template <> struct Row<KV_STUDENT_POW13> : RowStudentPow<13> {};
 
 template <>
 struct Row<2> {  // Plackett (the reference's formula, plackett.py:66-69), u = row, v = column

@@ -40,9 +40,18 @@ __device__ __forceinline__ double exp2_fast(double t) {
 
 // 2^t through a 256-entry table of 2^(i/256) (shared memory) and a degree-4 polynomial on |r| <= 2^-9:
 // 8 FP64 instructions instead of 13.  Same argument contract as exp2_fast.
-constexpr int EXPTAB_BITS = 8;
+#ifndef CVAR_EXPTAB_BITS
+#define CVAR_EXPTAB_BITS 8   // 10 (with the degree-3 polynomial) measured 4 % slower: the larger table costs more shared-memory wavefronts
+#endif
+constexpr int EXPTAB_BITS = CVAR_EXPTAB_BITS;
 constexpr int EXPTAB_SIZE = 1 << EXPTAB_BITS;
+#if CVAR_EXPTAB_BITS >= 10
+#define CVAR_EXP2_TAB_POLY_DEG CVAR_EXP2_TINY_POLY_DEG
+__constant__ double kExp2SmallCoef[CVAR_EXP2_TINY_POLY_DEG + 1] = CVAR_EXP2_TINY_POLY;
+#else
+#define CVAR_EXP2_TAB_POLY_DEG CVAR_EXP2_SMALL_POLY_DEG
 __constant__ double kExp2SmallCoef[CVAR_EXP2_SMALL_POLY_DEG + 1] = CVAR_EXP2_SMALL_POLY;
+#endif
 
 __global__ void exptab_build_kernel(double* __restrict__ tab) {
     const int i = threadIdx.x;
@@ -50,13 +59,13 @@ __global__ void exptab_build_kernel(double* __restrict__ tab) {
 }
 
 __device__ __forceinline__ double exp2_tab(double t, const double* __restrict__ tab) {
-    const double MAGIC = 6755399441055744.0 / EXPTAB_SIZE;  // rounds t to the nearest multiple of 2^-8
+    const double MAGIC = 6755399441055744.0 / EXPTAB_SIZE;  // rounds t to the nearest multiple of 2^-EXPTAB_BITS
     const double kf = __dadd_rn(t, MAGIC);
-    const int k256 = __double2loint(kf);                     // round(t * 256), two's complement
-    const double r = __dadd_rn(t, -__dadd_rn(kf, -MAGIC));   // |r| <= 2^-9, exact
-    double p = kExp2SmallCoef[CVAR_EXP2_SMALL_POLY_DEG];
+    const int k256 = __double2loint(kf);                     // round(t * 2^EXPTAB_BITS), two's complement
+    const double r = __dadd_rn(t, -__dadd_rn(kf, -MAGIC));   // |r| <= 2^-(EXPTAB_BITS+1), exact
+    double p = kExp2SmallCoef[CVAR_EXP2_TAB_POLY_DEG];
 #pragma unroll
-    for (int i = CVAR_EXP2_SMALL_POLY_DEG - 1; i >= 0; --i) p = fma(p, r, kExp2SmallCoef[i]);
+    for (int i = CVAR_EXP2_TAB_POLY_DEG - 1; i >= 0; --i) p = fma(p, r, kExp2SmallCoef[i]);
     const double v = tab[k256 & (EXPTAB_SIZE - 1)] * p;      // in [1, 2.01)
     const int k = max(k256 >> EXPTAB_BITS, -1021);
     return __hiloint2double(__double2hiint(v) + (k << 20), __double2loint(v));
@@ -112,13 +121,14 @@ __device__ __forceinline__ double log2_fast(double t) {
 constexpr int LOGTAB_BITS = 7;
 constexpr int LOGTAB_SIZE = 1 << LOGTAB_BITS;
 
-__device__ __forceinline__ double logtab_recip(int idx) {
-    // reciprocal of the midpoint of mantissa interval idx, exactly as the cell loop obtains it
-    const double mid = __hiloint2double(0x3ff00000 | (idx << (20 - LOGTAB_BITS)) | (1 << (19 - LOGTAB_BITS)), 0);
+__device__ __forceinline__ double seed_recip(int idx, int bits) {
+    // reciprocal of the midpoint of mantissa interval idx (of 2^bits), exactly as the cell loop obtains it
+    const double mid = __hiloint2double(0x3ff00000 | (idx << (20 - bits)) | (1 << (19 - bits)), 0);
     double r;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(mid));
     return r;
 }
+__device__ __forceinline__ double logtab_recip(int idx) { return seed_recip(idx, LOGTAB_BITS); }
 
 __global__ void logtab_build_kernel(double c, double* __restrict__ tab) {
     const int i = threadIdx.x;
@@ -143,46 +153,53 @@ __device__ __forceinline__ double scaled_log2_plus(double t, double b, double c,
 }
 
 // ----- table-assisted  t^(-c)  for the Student-t cell (no log, no exp) ---------------------------------
-// With t = 2^e * m and r_i the seed reciprocal of m's interval midpoint, m = (1 + f) / r_i, so
+// With t = 2^e * m and r_i the seed reciprocal (MUFU.RCP64H) of the midpoint of m's interval (the top POW_BITS
+// mantissa bits), m = (1 + f) / r_i with |f| <= 2^-(POW_BITS+1), so
 //     t^(-c) = 2^(-c e) * r_i^c * (1 + f)^(-c).
-// 2^(-c e) and r_i^c come from two small per-plan tables (POW_ETAB + POW_MTAB doubles in shared memory) and
-// (1 + f)^(-c) is its binomial series in f (|f| <= 2^-8), whose degree the plan picks from c:
-// 1 + DEG + 2 FP64 instructions in total instead of ~17 for c*log2(t) followed by exp2.
-constexpr int POW_MTAB = LOGTAB_SIZE;  // same mantissa intervals and seed reciprocals as the log2 table
+// 2^(-c e) and r_i^c come from two per-plan tables in shared memory (POW_ETAB + POW_MTAB doubles) and (1 + f)^(-c)
+// is a near-minimax polynomial in f that the plan fits for its c (Chebyshev interpolation, cvar_api.cu) at the
+// smallest degree with a relative error below 1e-15: degree 5 for nu <= 8, 6 up to nu = 30, 7 up to 50, 8 up to 100.
+// Larger tables need lower degrees but their lookups broadcast less (more shared-memory wavefronts per warp).
+// 3 + DEG FP64 instructions in total instead of ~17 for c*log2(t) followed by exp2.
+#ifndef CVAR_POW_BITS
+#define CVAR_POW_BITS 8    // measured on B200 (c3 / c2, ms): 7 bits 2.07 / 1.41, 8 bits 1.99 / 1.42, 9 bits 2.03 / 1.44, 10 bits 2.10 / 1.46
+#endif
+constexpr int POW_BITS = CVAR_POW_BITS;
+constexpr int POW_MTAB = 1 << POW_BITS;
 constexpr int POW_ETAB = 64;           // exponents 0..63 (t >= 1 always: t = C0 + d^2)
-constexpr int POW_MAX_DEG = 13;
+constexpr int POW_MAX_DEG = 8;
+constexpr double POW_FMAX = 1.03 / (1 << (POW_BITS + 1));   // |f| bound incl. the seed's own error
 
 __global__ void powtab_build_kernel(double c, double* __restrict__ tab) {
     const int i = threadIdx.x;
-    if (i < POW_MTAB) tab[i] = pow(logtab_recip(i), c);
+    if (i < POW_MTAB) tab[i] = pow(seed_recip(i, POW_BITS), c);
     if (i < POW_ETAB) tab[POW_MTAB + i] = exp2(-c * (double)i);
 }
 
-// Requires 1 <= t < 2^POW_ETAB (stage 0 clamps the Student-t quantiles so that this holds, see KernelParams::y_max):
-// the exponent table is indexed without a range check.  Index arithmetic stays "in place": the masked mantissa
-// and exponent fields of t's high word are shifted straight into byte offsets, one integer op each.
 __device__ __forceinline__ double lds_f64(unsigned shared_addr) {
     double v;
     asm("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(shared_addr));
     return v;
 }
 
-// `tab_s` is the shared-window address of the table (cvta.to.shared, hoisted by the caller): with a generic pointer
-// ptxas rebuilds the address from two loop-invariant halves for every lookup
+// Requires 1 <= t < 2^POW_ETAB (stage 0 clamps the Student-t quantiles so that this holds, see KernelParams::y_max):
+// the exponent table is indexed without a range check.  Index arithmetic stays "in place": the masked mantissa
+// and exponent fields of t's high word are shifted straight into byte offsets, one integer op each.  `tab_s` is the
+// shared-window address of the table (cvta.to.shared, hoisted by the caller): with a generic pointer ptxas rebuilds
+// the address from two loop-invariant halves for every lookup.
 template <int DEG>
 __device__ __forceinline__ double pow_neg_c(double t, const double* __restrict__ kc, unsigned tab_s) {
     const unsigned hi = (unsigned)__double2hiint(t);
-    const unsigned mb = hi & (unsigned)((POW_MTAB - 1) << (20 - LOGTAB_BITS));  // interval index, still at bit 13
-    const unsigned eb = hi & 0x7ff00000u;                                       // biased exponent, still at bit 20
-    double r;  // == logtab_recip(idx)
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(__hiloint2double((int)(mb | 0x3ff00000u | (1u << (19 - LOGTAB_BITS))), 0)));
-    r = __hiloint2double(__double2hiint(r) - (int)eb + 0x3ff00000, 0);          // r_i * 2^-e
+    const unsigned mb = hi & (unsigned)((POW_MTAB - 1) << (20 - POW_BITS));   // interval index, still in place
+    const unsigned eb = hi & 0x7ff00000u;                                     // biased exponent, still at bit 20
+    double r;  // == seed_recip(idx, POW_BITS)
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(__hiloint2double((int)(mb | 0x3ff00000u | (1u << (19 - POW_BITS))), 0)));
+    r = __hiloint2double(__double2hiint(r) - (int)eb + 0x3ff00000, 0);        // r_i * 2^-e
     const double f = fma(t, r, -1.0);
     double p = kc[DEG];
 #pragma unroll
-    for (int k = DEG - 1; k >= 1; --k) p = fma(p, f, kc[k]);
-    p = fma(p, f, 1.0);
-    const double pm = lds_f64(tab_s + (mb >> (20 - LOGTAB_BITS - 3)));
+    for (int k = DEG - 1; k >= 0; --k) p = fma(p, f, kc[k]);
+    const double pm = lds_f64(tab_s + (mb >> (20 - POW_BITS - 3)));
     const double pe = lds_f64(tab_s + (unsigned)((POW_MTAB - 1023) * 8) + (eb >> 17));
     return (pm * pe) * p;
 }

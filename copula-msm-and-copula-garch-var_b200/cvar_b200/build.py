@@ -42,7 +42,8 @@ def build_library(force: bool = False, verbose: bool = False) -> Path:
     """Compile csrc/*.cu into libcvar_b200.so (sm_100a). Returns the library path."""
     if not force and not is_stale():
         return LIB_PATH
-    cmd = [_nvcc(), *NVCC_FLAGS, *(["-Xptxas", "-v"] if verbose else []), "-o", str(LIB_PATH),
+    extra = os.environ.get("CVAR_NVCC_EXTRA", "").split()   # tuning knob, e.g. "-DCVAR_POW_BITS=8"
+    cmd = [_nvcc(), *NVCC_FLAGS, *extra, *(["-Xptxas", "-v"] if verbose else []), "-o", str(LIB_PATH),
            *[str(CSRC / s) for s in SOURCES]]
     proc = subprocess.run(cmd, capture_output=True, text=True)
     if proc.returncode != 0:

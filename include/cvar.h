@@ -71,7 +71,7 @@ extern "C" {
 #define CVAR_ERR_SMEM (-8)          /* grid too large for the shared memory of one SM    */
 
 #define CVAR_MAX_N 8192 /* hard cap; this version keeps a day's axis data in one SM's shared memory, which
-                           limits n to ~4200 on B200 (cvar_plan_create returns CVAR_ERR_SMEM beyond) */
+                           limits n to ~4900 on B200 (cvar_plan_create returns CVAR_ERR_SMEM beyond) */
 #define CVAR_MAX_Q 32
 #define CVAR_MAX_ALPHA 8
 #define CVAR_MAX_ITER 30
@@ -127,7 +127,7 @@ typedef struct cvar_plan_info {
                                     over 4 off-node probes per table interval; 0 otherwise */
     double last_kernel_ms;     /* device time of the last *_host solve (CUDA events), ms */
     int32_t kernel_variant;    /* 0 Gaussian, 1 Student-t (generic log2/exp2 cell), 2 Plackett, 3/4/5/6 Student-t with the
-                                  table-assisted power cell of degree 6/8/10/13 (picked from nu at plan creation) */
+                                  table-assisted power cell of degree 5/6/7/8 (picked from nu at plan creation) */
     int32_t reserved;
 } cvar_plan_info_t;
 
