@@ -30,6 +30,8 @@ struct cvar_plan {
     int ctas_per_sm;
     int cta_threads;
     bool cta_threads_forced;  // CVAR_CTA_THREADS was given: no launch-time adjustment
+    int cluster_forced;       // CVAR_CLUSTER = 1, 2 or 4: fixed cluster size (0: chosen per launch)
+    int max_clusters[5];      // [2], [4]: clusters of that size that can be co-resident (cudaOccupancyMaxActiveClusters)
     size_t smem_bytes;
     double tq_err;
     double last_kernel_ms;
@@ -191,15 +193,50 @@ int launch_threads(const cvar_plan* p, int64_t T) {
     return p->cta_threads;
 }
 
+// A batch that cannot even give every second (fourth) SM a day is split further: 2 or 4 CTAs of a thread-block
+// cluster share one day (cvar_kernels.cuh, `Part`).  Measured at n = 2048: see DESIGN.md section 8.
+int cluster_size(const cvar_plan* p, int64_t T) {
+    if (p->cluster_forced > 0) return p->cluster_forced;
+    if (p->cta_threads_forced || p->kp.n < 1024) return 1;
+    if (T <= p->max_clusters[4]) return 4;   // only while every cluster of the batch is resident at once
+    if (T <= p->max_clusters[2]) return 2;
+    return 1;
+}
+
+template <typename K>
+int launch_clustered(K kernel, int cluster, unsigned grid, unsigned block, size_t smem, cudaStream_t st, KernelParams kp,
+                     const double* d_day, long long T, AlphaSet A, const int* order, unsigned* traj, double* mass,
+                     unsigned long long* cells) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(block);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)cluster;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return (int)cudaLaunchKernelEx(&cfg, kernel, kp, d_day, T, A, order, traj, mass, cells);
+}
+
 int launch_solve(cvar_plan* p, const double* d_day, int64_t T, const AlphaSet& A, uint32_t* d_traj, double* d_mass,
                  unsigned long long* d_cells, cudaStream_t st) {
     if (T == 0) return 0;
     const int* order = nullptr;
     int rc = make_order(p, d_day, T, st, &order);
     if (rc) return rc;
+    const int cluster = cluster_size(p, T);
     dim3 grid((unsigned)T), block(launch_threads(p, T));
-#define CVAR_LAUNCH_SOLVE(KV) \
-    case KV: solve_kernel<KV><<<grid, block, p->smem_bytes, st>>>(p->kp, d_day, (long long)T, A, order, d_traj, d_mass, d_cells); break;
+#define CVAR_LAUNCH_SOLVE(KV)                                                                                              \
+    case KV:                                                                                                               \
+        if (cluster > 1)                                                                                                   \
+            return launch_clustered(solve_kernel<KV, true>, cluster, (unsigned)(T * cluster), block.x, p->smem_bytes, st, p->kp, \
+                                    d_day, (long long)T, A, order, d_traj, d_mass, d_cells);                              \
+        solve_kernel<KV, false><<<grid, block, p->smem_bytes, st>>>(p->kp, d_day, (long long)T, A, order, d_traj, d_mass, d_cells); \
+        break;
     switch (p->kernel_variant) {
         CVAR_LAUNCH_SOLVE(0) CVAR_LAUNCH_SOLVE(1) CVAR_LAUNCH_SOLVE(2) CVAR_LAUNCH_SOLVE(3) CVAR_LAUNCH_SOLVE(4) CVAR_LAUNCH_SOLVE(5)
         CVAR_LAUNCH_SOLVE(6)
@@ -501,12 +538,17 @@ int cvar_plan_create(const cvar_desc_t* desc, const double* x, const double* dx,
             p->cta_threads_forced = true;
         }
     }
+    if (const char* env = std::getenv("CVAR_CLUSTER")) {        // tuning knob: 1, 2 or 4 CTAs per day
+        const int v = std::atoi(env);
+        if (v == 1 || v == 2 || v == 4) p->cluster_forced = v;
+    }
 #define CVAR_PREP(KV)                                                                                              \
     case KV:                                                                                                       \
-        PLAN_TRY((cudaError_t)set_smem(solve_kernel<KV>, p->smem_bytes));                                          \
+        PLAN_TRY((cudaError_t)set_smem(solve_kernel<KV, false>, p->smem_bytes));                                   \
+        PLAN_TRY((cudaError_t)set_smem(solve_kernel<KV, true>, p->smem_bytes));                                    \
         PLAN_TRY((cudaError_t)set_smem(strip_mass_kernel<KV>, p->smem_bytes));                                     \
         for (int attempt = 0; attempt < 2; ++attempt) {                                                            \
-            PLAN_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, solve_kernel<KV>, p->cta_threads, p->smem_bytes)); \
+            PLAN_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, solve_kernel<KV, false>, p->cta_threads, p->smem_bytes)); \
             if (occ >= 2 || attempt == 1) break;                                                                   \
             p->cta_threads = CTA_THREADS_LARGE; /* only one CTA fits an SM: give it 16 warps */                    \
         }                                                                                                          \
@@ -517,6 +559,32 @@ int cvar_plan_create(const cvar_desc_t* desc, const double* x, const double* dx,
     }
 #undef CVAR_PREP
     p->ctas_per_sm = occ;
+    // how many 2- and 4-CTA clusters of the large CTA fit the device at once (GPC boundaries make this less than
+    // #SMs / size); a failure here only disables the cluster split
+#define CVAR_CLUSTER_OCC(KV)                                                                              \
+    case KV:                                                                                              \
+        for (int cs = 2; cs <= 4; cs *= 2) {                                                              \
+            cudaLaunchConfig_t cfg = {};                                                                  \
+            cfg.gridDim = dim3((unsigned)(cs * p->sm_count));                                             \
+            cfg.blockDim = dim3(CTA_THREADS_LARGE);                                                       \
+            cfg.dynamicSmemBytes = p->smem_bytes;                                                         \
+            cudaLaunchAttribute attr[1];                                                                  \
+            attr[0].id = cudaLaunchAttributeClusterDimension;                                             \
+            attr[0].val.clusterDim.x = (unsigned)cs;                                                      \
+            attr[0].val.clusterDim.y = attr[0].val.clusterDim.z = 1;                                      \
+            cfg.attrs = attr;                                                                             \
+            cfg.numAttrs = 1;                                                                             \
+            int num = 0;                                                                                  \
+            if (cudaOccupancyMaxActiveClusters(&num, solve_kernel<KV, true>, &cfg) == cudaSuccess) p->max_clusters[cs] = num; \
+            else cudaGetLastError();                                                                      \
+        }                                                                                                 \
+        break;
+    switch (p->kernel_variant) {
+        CVAR_CLUSTER_OCC(0) CVAR_CLUSTER_OCC(1) CVAR_CLUSTER_OCC(2) CVAR_CLUSTER_OCC(3) CVAR_CLUSTER_OCC(4) CVAR_CLUSTER_OCC(5)
+        CVAR_CLUSTER_OCC(6)
+        default: break;
+    }
+#undef CVAR_CLUSTER_OCC
 #undef PLAN_TRY
     *out = p;
     return CVAR_OK;
@@ -556,7 +624,7 @@ int cvar_plan_get_info(const cvar_plan_t* p, cvar_plan_info_t* info) {
     info->tq_table_max_rel_err = p->tq_err;
     info->last_kernel_ms = p->last_kernel_ms;
     info->kernel_variant = p->kernel_variant;
-    info->reserved = 0;
+    info->cluster4_capacity = p->max_clusters[4];
     return CVAR_OK;
 }
 

@@ -15,6 +15,8 @@
 // identical to the reference's; only the cell *weights* are computed in a restructured (per-axis
 // factored) form.
 #pragma once
+#include <cooperative_groups.h>
+
 #include "cvar_math.cuh"
 
 namespace cvar {
@@ -99,6 +101,8 @@ struct Smem {
     double* red;    // [2][MAX_CTA_WARPS]
     unsigned* redc; // [2][MAX_CTA_WARPS]
     int* live;      // [4]: dead-prefix / dead-suffix counts per axis
+    double* cl_mass;    // [2] this CTA's strip partial, read by the other CTAs of a cluster
+    unsigned* cl_cells; // [2]
     double* ltab;   // [LOGTAB_SIZE] student only
     double* etab;   // [EXPTAB_SIZE] gaussian / student
     double* memo;   // [MEMO_SIZE][4]: (lo, hi, mass, cells) of strips already integrated for an earlier alpha
@@ -135,6 +139,8 @@ __device__ __forceinline__ Smem carve(unsigned char* base, int n, int kv) {
     S.c[2] = h + 2 * npad;
     S.redc = reinterpret_cast<unsigned*>(h + 3 * npad);
     S.live = reinterpret_cast<int*>(S.redc + 2 * MAX_CTA_WARPS);
+    S.cl_mass = reinterpret_cast<double*>(S.live + 4);    // live[4] | cl_mass[2] | cl_cells[2] | pad: 64 bytes in all
+    S.cl_cells = reinterpret_cast<unsigned*>(S.live + 8);
     S.memo = reinterpret_cast<double*>(S.live + 4 + 12);  // 64 bytes after `live`: stays 8-byte aligned
     double* tables = S.memo + MEMO_SIZE * 4;              // variant-specific tables, see table_doubles()
     S.ltab = tables;                                      // KV_STUDENT: ltab then etab
@@ -274,13 +280,24 @@ __device__ __forceinline__ int count_le(const double* __restrict__ xs, double g,
 // the strip length falls off monotonically with the row index and a fixed order would always hand warp 0
 // the longest rows.  The mapping is fixed for the whole solve: a thread only ever touches its own rows'
 // boundary entries, which is why no barrier separates the boundary search from the cell walk.
-__device__ __forceinline__ int owned_row(int m) {
-    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-    const int nw = blockDim.x >> 5;
+//
+// A day can also be split over a thread-block CLUSTER (small batches, see solve_kernel): the warps of all CTAs of the
+// cluster then form one pool (`Part`), every CTA owns the rows of its warps, and the strip masses are combined
+// through distributed shared memory (block_reduce).
+struct Part {
+    int rank, size;  // this CTA's rank in the cluster and the cluster size (0, 1 without a cluster)
+};
+
+__device__ __forceinline__ int owned_row(const Part& pt, int m) {
+    const int w = pt.rank * (blockDim.x >> 5) + (threadIdx.x >> 5), l = threadIdx.x & 31;
+    const int nw = pt.size * (blockDim.x >> 5);
     const int wb = (m & 1) ? (nw - 1 - w) : w;
     return ((m * nw + wb) << 5) + l;
 }
-__device__ __forceinline__ int owned_rounds(int n) { return (n + blockDim.x - 1) / blockDim.x; }
+__device__ __forceinline__ int owned_rounds(const Part& pt, int n) {
+    const int per = pt.size * blockDim.x;
+    return (n + per - 1) / per;
+}
 
 // c = max(#{x <= g_i(q)}, cmin) for outer row i; the search is confined to [lo, hi]
 __device__ __forceinline__ int count_row(const KernelParams& P, const Smem& S, double q, int i, int lo, int hi) {
@@ -290,11 +307,11 @@ __device__ __forceinline__ int count_row(const KernelParams& P, const Smem& S, d
 }
 
 // ctarget[i] = count_row(q) for every outer row this thread owns
-__device__ __forceinline__ void count_rows(const KernelParams& P, const Smem& S, double q, u16* ctarget,
+__device__ __forceinline__ void count_rows(const KernelParams& P, const Smem& S, const Part& pt, double q, u16* ctarget,
                                            const u16* slo, const u16* shi) {
     const int n = P.n;
-    for (int m = 0; m < owned_rounds(n); ++m) {
-        const int i = owned_row(m);
+    for (int m = 0; m < owned_rounds(pt, n); ++m) {
+        const int i = owned_row(pt, m);
         if (i < n) ctarget[i] = (u16)count_row(P, S, q, i, slo ? (int)slo[i] : 0, shi ? (int)shi[i] : n);
     }
 }
@@ -385,8 +402,10 @@ struct Live {  // live window of rows / columns (cells outside have an infinite 
     int i_lo, i_hi, j_lo, j_hi;
 };
 
-// block-wide deterministic sum; every thread receives the same value
-__device__ __forceinline__ StripResult block_reduce(const Smem& S, int& parity, double v, unsigned cells, bool poison) {
+// block-wide (cluster-wide when the day is split over a cluster) deterministic sum; every thread of every CTA
+// receives the same value
+__device__ __forceinline__ StripResult block_reduce(const Smem& S, const Part& pt, int& parity, double v, unsigned cells,
+                                                    bool poison) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -405,6 +424,27 @@ __device__ __forceinline__ StripResult block_reduce(const Smem& S, int& parity, 
         r.cells += S.redc[parity * MAX_CTA_WARPS + w];
     }
     r.poisoned = anyp != 0;
+    if (pt.size > 1) {
+        // publish this CTA's partial, then read every CTA's slot in rank order through distributed shared memory.
+        // The slots are double-buffered by `parity`: a slot is rewritten two strips later, after the cluster barrier
+        // of the strip in between, which every CTA only passes once it has read the current values.
+        namespace cg = cooperative_groups;
+        cg::cluster_group cluster = cg::this_cluster();
+        if (threadIdx.x == 0) {
+            S.cl_mass[parity] = r.poisoned ? NAN : r.mass;   // a poisoned strip is NaN for the whole cluster
+            S.cl_cells[parity] = r.cells;
+        }
+        cluster.sync();
+        double tot = 0.0;
+        unsigned cel = 0;
+        for (int k = 0; k < pt.size; ++k) {
+            tot += cluster.map_shared_rank(S.cl_mass, k)[parity];
+            cel += cluster.map_shared_rank(S.cl_cells, k)[parity];
+        }
+        r.mass = tot;
+        r.cells = cel;
+        r.poisoned = tot != tot;
+    }
     parity ^= 1;
     return r;
 }
@@ -420,7 +460,7 @@ __device__ __forceinline__ StripResult block_reduce(const Smem& S, int& parity, 
 //   bound arrays: ca == nullptr means the constant lower end cmin; cnew (may alias ca or cb) receives
 //   count(q_new) searched inside [slo[i], shi[i]] before the row is summed.
 template <int COPULA>
-__device__ StripResult strip_pass(const KernelParams& P, const Smem& S, const Live& L, int& parity, bool do_count,
+__device__ StripResult strip_pass(const KernelParams& P, const Smem& S, const Part& pt, const Live& L, int& parity, bool do_count,
                                   double q_new, u16* cnew, const u16* slo, const u16* shi, const u16* ca,
                                   const u16* cb, bool poison_mode) {
     constexpr int CELLS_IN_FLIGHT = CellsInFlight<COPULA>::value;
@@ -428,8 +468,8 @@ __device__ StripResult strip_pass(const KernelParams& P, const Smem& S, const Li
     double total = 0.0;
     unsigned cells = 0;
     bool poison = false;
-    for (int m = 0; m < owned_rounds(n); ++m) {
-        const int i = owned_row(m);
+    for (int m = 0; m < owned_rounds(pt, n); ++m) {
+        const int i = owned_row(pt, m);
         if (i >= n) continue;
         if (do_count) {
             const int lo = slo ? (int)slo[i] : 0, hi = shi ? (int)shi[i] : n;
@@ -473,7 +513,7 @@ __device__ StripResult strip_pass(const KernelParams& P, const Smem& S, const Li
         for (int c = 1; c < CELLS_IN_FLIGHT; ++c) rowsum += acc[c];
         total = fma(row.fac, rowsum, total);
     }
-    StripResult r = block_reduce(S, parity, total, cells, poison && poison_mode);
+    StripResult r = block_reduce(S, pt, parity, total, cells, poison && poison_mode);
     if (r.poisoned) r.mass = NAN;
     return r;
 }
@@ -482,7 +522,7 @@ __device__ StripResult strip_pass(const KernelParams& P, const Smem& S, const Li
 // so far (by thread 0, right after a strip's reduction); only the first `memo_visible` of them -- those of
 // earlier alphas, published by the barrier at the top of the alpha loop -- are searched.
 template <int COPULA>
-__device__ __forceinline__ StripResult strip_memo(const KernelParams& P, const Smem& S, const Live& L, int& parity,
+__device__ __forceinline__ StripResult strip_memo(const KernelParams& P, const Smem& S, const Part& pt, const Live& L, int& parity,
                                                   bool use_memo, bool remember, int memo_visible, int& memo_n,
                                                   double a, double b,
                                                   double q_new, u16* cnew, const u16* slo, const u16* shi,
@@ -491,7 +531,7 @@ __device__ __forceinline__ StripResult strip_memo(const KernelParams& P, const S
         for (int k = 0; k < memo_visible; ++k) {
             const double* e = S.memo + 4 * k;
             if (e[0] == a && e[1] == b) {
-                count_rows(P, S, q_new, cnew, slo, shi);  // the boundary indices are still needed downstream
+                count_rows(P, S, pt, q_new, cnew, slo, shi);  // the boundary indices are still needed downstream
                 StripResult r;
                 r.mass = e[2];
                 r.cells = (unsigned)e[3];
@@ -500,7 +540,7 @@ __device__ __forceinline__ StripResult strip_memo(const KernelParams& P, const S
             }
         }
     }
-    const StripResult r = strip_pass<COPULA>(P, S, L, parity, true, q_new, cnew, slo, shi, ca, cb, poison_mode);
+    const StripResult r = strip_pass<COPULA>(P, S, pt, L, parity, true, q_new, cnew, slo, shi, ca, cb, poison_mode);
     if (use_memo && remember && memo_n < MEMO_SIZE) {
         if (threadIdx.x == 0) {
             double* e = S.memo + 4 * memo_n;
@@ -514,15 +554,24 @@ __device__ __forceinline__ StripResult strip_memo(const KernelParams& P, const S
 // ---------------------------------------------------------------------------------------------
 // the solve kernel
 // ---------------------------------------------------------------------------------------------
-template <int COPULA>
+// CLUSTER = true: launched with a cluster dimension of 2 or 4 -- the CTAs of a cluster share one day (each runs
+// stage 0 for itself, owns a share of the outer rows and sees the same strip masses, hence takes the same decisions).
+template <int COPULA, bool CLUSTER>
 __global__ void __launch_bounds__(CTA_THREADS_LARGE, 1)
 solve_kernel(KernelParams P, const double* __restrict__ day_params, long long T, AlphaSet A,
              const int* __restrict__ order, unsigned* __restrict__ traj, double* __restrict__ mass_out,
              unsigned long long* __restrict__ cells_out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const Smem S = carve(smem_raw, P.n, COPULA);
+    Part pt = {0, 1};
+    if (CLUSTER) {
+        cooperative_groups::cluster_group cluster = cooperative_groups::this_cluster();
+        pt.rank = (int)cluster.block_rank();
+        pt.size = (int)cluster.num_blocks();
+    }
     // CTAs are dispatched in block-index order; `order` lists the days most expensive first (see order_key_kernel)
-    const long long day = order ? order[blockIdx.x] : blockIdx.x;
+    const long long unit = blockIdx.x / pt.size;
+    const long long day = order ? order[unit] : unit;
     const int stride = (P.marginal == 0) ? 2 : 2 * P.q;
     stage0<COPULA>(P, day_params + day * stride, S);
 
@@ -549,10 +598,10 @@ solve_kernel(KernelParams P, const double* __restrict__ day_params, long long T,
         const int memo_visible = memo_n;
         // --- probe 1: F(first)  (calc_var_class.py:114-119)
         if (!have_f3) {
-            f3 = strip_pass<COPULA>(P, S, L, parity, true, P.first, S.c[0], nullptr, nullptr, nullptr, S.c[0], poison_mode);
+            f3 = strip_pass<COPULA>(P, S, pt, L, parity, true, P.first, S.c[0], nullptr, nullptr, nullptr, S.c[0], poison_mode);
             have_f3 = true;
         } else {
-            count_rows(P, S, P.first, S.c[0], nullptr, nullptr);
+            count_rows(P, S, pt, P.first, S.c[0], nullptr, nullptr);
         }
         ncell += f3.cells;
         // --- probe 2  (:125-142)
@@ -561,10 +610,10 @@ solve_kernel(KernelParams P, const double* __restrict__ day_params, long long T,
         double prev_upper = (lo2 == P.second_lo) ? P.second_lo : P.first;  // Q6
         StripResult s2;
         if (lo2 == P.first)   // strip (first, second_hi]: new upper boundary, searched above c[0]
-            s2 = strip_memo<COPULA>(P, S, L, parity, use_memo, true, memo_visible, memo_n, lo2, hi2, hi2, S.c[1], S.c[0], nullptr,
+            s2 = strip_memo<COPULA>(P, S, pt, L, parity, use_memo, true, memo_visible, memo_n, lo2, hi2, hi2, S.c[1], S.c[0], nullptr,
                                     S.c[0], S.c[1], poison_mode);
         else                  // strip (second_lo, first]: new lower boundary, searched below c[0]
-            s2 = strip_memo<COPULA>(P, S, L, parity, use_memo, true, memo_visible, memo_n, lo2, hi2, lo2, S.c[1], nullptr, S.c[0],
+            s2 = strip_memo<COPULA>(P, S, pt, L, parity, use_memo, true, memo_visible, memo_n, lo2, hi2, lo2, S.c[1], nullptr, S.c[0],
                                     S.c[1], S.c[0], poison_mode);
         ncell += s2.cells;
         double R = (lo2 == P.first) ? f3.mass + s2.mass : f3.mass - s2.mass;
@@ -577,12 +626,12 @@ solve_kernel(KernelParams P, const double* __restrict__ day_params, long long T,
             kase = 3; lo = P.first; hi = P.second_hi; cl = S.c[0]; ch = S.c[1]; cm = S.c[2];
         } else if (R > alpha) {
             kase = 0; lo = P.min_var; hi = P.second_lo; ch = S.c[1]; cl = S.c[2]; cm = S.c[0];
-            count_rows(P, S, lo, cl, nullptr, ch);
+            count_rows(P, S, pt, lo, cl, nullptr, ch);
         } else if (R < alpha && hi2 == P.first) {
             kase = 1; lo = P.second_lo; hi = P.first; cl = S.c[1]; ch = S.c[0]; cm = S.c[2];
         } else if (R < alpha && hi2 == P.second_hi) {
             kase = 2; lo = P.second_hi; hi = P.max_var; cl = S.c[1]; ch = S.c[2]; cm = S.c[0];
-            count_rows(P, S, hi, ch, cl, nullptr);
+            count_rows(P, S, pt, hi, ch, cl, nullptr);
         } else {
             kase = 4; lo = hi = NAN; cl = ch = cm = S.c[0];
         }
@@ -592,7 +641,7 @@ solve_kernel(KernelParams P, const double* __restrict__ day_params, long long T,
             for (int k = 0; k < P.max_iter; ++k) {
                 const double mid = (lo + hi) / 2;
                 const double a = stack ? lo : mid, b = stack ? mid : hi;
-                const StripResult s = strip_memo<COPULA>(P, S, L, parity, use_memo, k < MEMO_PER_ALPHA - 1, memo_visible, memo_n, a, b,
+                const StripResult s = strip_memo<COPULA>(P, S, pt, L, parity, use_memo, k < MEMO_PER_ALPHA - 1, memo_visible, memo_n, a, b,
                                                          mid, cm, cl, ch, stack ? cl : cm, stack ? cm : ch, poison_mode);
                 ncell += s.cells;
                 R = (a == prev_upper) ? R + s.mass : R - s.mass;  // adjust_integral (:241-246)
@@ -603,7 +652,7 @@ solve_kernel(KernelParams P, const double* __restrict__ day_params, long long T,
                 prev_upper = mid;
             }
         }
-        if (threadIdx.x == 0) {
+        if (threadIdx.x == 0 && pt.rank == 0) {
             const long long o = (long long)ia * T + day;
             traj[2 * o] = dec | ((unsigned)kase << 28);
             traj[2 * o + 1] = zer;
@@ -611,6 +660,8 @@ solve_kernel(KernelParams P, const double* __restrict__ day_params, long long T,
             if (cells_out) cells_out[o] = ncell;
         }
     }
+    // no CTA may retire while a peer can still read its partial sums
+    if (CLUSTER) cooperative_groups::this_cluster().sync();
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -635,9 +686,10 @@ strip_mass_kernel(KernelParams P, const double* __restrict__ day_params, const d
     const bool poison_mode = (COPULA != 2) && (P.marginal == 1) && ((P.compat & 4u) != 0);
     int parity = 0;
     const double lo = bounds[2 * day], hi = bounds[2 * day + 1];
-    count_rows(P, S, lo, S.c[0], nullptr, nullptr);
+    const Part pt = {0, 1};
+    count_rows(P, S, pt, lo, S.c[0], nullptr, nullptr);
     // an inverted pair yields an empty strip (cb <= ca), like the reference's empty np.where
-    const StripResult s = strip_pass<COPULA>(P, S, L, parity, true, hi, S.c[1], nullptr, nullptr, S.c[0], S.c[1], poison_mode);
+    const StripResult s = strip_pass<COPULA>(P, S, pt, L, parity, true, hi, S.c[1], nullptr, nullptr, S.c[0], S.c[1], poison_mode);
     if (threadIdx.x == 0) {
         out[day] = s.mass;
         if (cells_out) cells_out[day] = s.cells;

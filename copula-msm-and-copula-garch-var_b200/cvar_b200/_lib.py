@@ -32,7 +32,7 @@ class CvarPlanInfo(C.Structure):
         ("device", C.c_int32), ("sm_count", C.c_int32), ("max_iter", C.c_int32), ("ctas_per_sm", C.c_int32),
         ("threads_per_cta", C.c_int32), ("smem_bytes_per_cta", C.c_int32),
         ("tq_table_max_rel_err", C.c_double), ("last_kernel_ms", C.c_double),
-        ("kernel_variant", C.c_int32), ("reserved", C.c_int32),
+        ("kernel_variant", C.c_int32), ("cluster4_capacity", C.c_int32),
     ]
 
 

@@ -128,7 +128,8 @@ typedef struct cvar_plan_info {
     double last_kernel_ms;     /* device time of the last *_host solve (CUDA events), ms */
     int32_t kernel_variant;    /* 0 Gaussian, 1 Student-t (generic log2/exp2 cell), 2 Plackett, 3/4/5/6 Student-t with the
                                   table-assisted power cell of degree 5/6/7/8 (picked from nu at plan creation) */
-    int32_t reserved;
+    int32_t cluster4_capacity; /* 4-CTA clusters of the solve kernel that can be resident at once: batches of at most
+                                  this many days are split four ways, up to about twice as many two ways (n >= 1024) */
 } cvar_plan_info_t;
 
 /* Fill *desc with the reference's defaults (everything except copula/marginal/n/q/params). */

@@ -148,3 +148,43 @@ def test_student_power_variants_agree_with_the_generic_cell(backend, monkeypatch
         slow = plan.solve(inp.day_params(), [0.01, 0.05])
     np.testing.assert_allclose(fast_mass, slow_mass, rtol=1e-13, atol=1e-16)
     assert fast.var.tobytes() == slow.var.tobytes()
+
+
+@pytest.mark.parametrize("copula,marginal", [("gaussian", "single"), ("student", "mixture"), ("plackett", "single")])
+@pytest.mark.parametrize("T,cluster", [(5, 4), (40, 2)])
+def test_cluster_split_days_equal_single_cta_days(backend, monkeypatch, cuda_device, copula, marginal, T, cluster):
+    """Small batches split a day over a 2- or 4-CTA thread-block cluster (row blocks per CTA, strip masses combined
+    through distributed shared memory).  Decisions, brackets and cell counts must equal the one-CTA-per-day launch;
+    final masses agree to summation-order rounding."""
+    import torch
+    from cvar_b200 import synthetic as syn
+    from cvar_b200.inputs import make_inputs
+    n = 1024
+    if marginal == "single":
+        inp = make_inputs(copula, "single", n, rho=0.6, nu=5.3, theta=4.2, sigma=syn.garch_sigma_path(T))
+    else:
+        inp, _ = syn.baseline_config("c3", T=T, n=n)
+    alphas = [0.01, 0.05]
+    day = torch.from_numpy(inp.day_params()).to(cuda_device)
+
+    def run(force):
+        if force is None:
+            monkeypatch.delenv("CVAR_CLUSTER", raising=False)
+        else:
+            monkeypatch.setenv("CVAR_CLUSTER", str(force))
+        with backend.VarPlan(inp) as plan:
+            mass = torch.empty((2, T), dtype=torch.float64, device=cuda_device)
+            cells = torch.empty((2, T), dtype=torch.int64, device=cuda_device)
+            traj = plan.solve_device(day, alphas, mass=mass, cells=cells)
+            var, case, iters = plan.finalize_device(traj)
+            torch.cuda.synchronize()
+            return traj.cpu().numpy(), mass.cpu().numpy(), cells.cpu().numpy(), var.cpu().numpy(), case.cpu().numpy()
+
+    auto = run(None)                 # T <= #SMs / cluster  ->  clusters of `cluster` CTAs
+    forced = run(cluster)
+    single = run(1)
+    for got in (auto, forced):
+        assert np.array_equal(got[0], single[0]) and np.array_equal(got[2], single[2]) and np.array_equal(got[4], single[4])
+        assert got[3].tobytes() == single[3].tobytes()
+        np.testing.assert_allclose(got[1], single[1], rtol=1e-13, atol=1e-18)
+    assert auto[1].tobytes() == forced[1].tobytes()          # the automatic choice is the expected cluster size
