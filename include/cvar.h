@@ -132,6 +132,15 @@ typedef struct cvar_plan_info {
                                   this many days are split four ways, up to about twice as many two ways (n >= 1024) */
 } cvar_plan_info_t;
 
+/*
+ * Environment knobs read at cvar_plan_create (tuning and tests; defaults are measured choices):
+ *   CVAR_CTA_THREADS=32..512   fixed CTA size of the solve / strip kernels (disables the launch-time choices below)
+ *   CVAR_CLUSTER=1|2|4         fixed number of CTAs (thread-block cluster) per day; default: 4 / 2 while the whole batch
+ *                              stays resident (n >= 1024), else 1
+ *   CVAR_STUDENT_GENERIC=1     Student-t plans use the generic log2/exp2 cell instead of the table-assisted power cell
+ * The Python loader additionally honours CVAR_B200_LIB=<path to an alternative libcvar_b200.so>.
+ */
+
 /* Fill *desc with the reference's defaults (everything except copula/marginal/n/q/params). */
 void cvar_desc_default(cvar_desc_t* desc);
 
