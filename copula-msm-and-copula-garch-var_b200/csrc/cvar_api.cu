@@ -511,6 +511,8 @@ int cvar_plan_create(const cvar_desc_t* desc, const double* x, const double* dx,
         constexpr double q1p[] = CVAR_LOG2_1P_POLY;
         kp.negc = -0.5 * (desc->nu + 2.0);
         kp.inv_nu = 1.0 / desc->nu;
+        kp.seed_mask = ~((1u << (20 - POW_BITS)) - 1u);
+        kp.seed_half = 1u << (19 - POW_BITS);
         for (int k = 0; k <= CVAR_LOG2_1P_POLY_DEG; ++k) kp.qc[k] = kp.negc * q1p[k];
         PLAN_TRY(cudaMalloc(&p->d_logtab, sizeof(double) * LOGTAB_SIZE));
         logtab_build_kernel<<<1, LOGTAB_SIZE, 0, p->stream>>>(kp.negc, p->d_logtab);

@@ -72,6 +72,7 @@ struct KernelParams {
     double tq_tail_lc;   // student: log of the leading tail coefficient
     double negc;         // student: -(nu+2)/2, the exponent of the quadratic form
     double inv_nu;       // student: 1/nu
+    unsigned seed_mask, seed_half;  // student pow variants: keep sign/exponent/top POW_BITS mantissa bits | interval midpoint bit
     double y_max;        // student pow variants: clamp of |T_nu^-1(u)| that keeps the quadratic form below 2^63
     double qc[CVAR_LOG2_1P_POLY_DEG + 1];  // student: negc * coefficients of log2(1+f)/f
     const double* logtab;  // student: negc * (-log2 r_i), LOGTAB_SIZE entries (global; staged to shared memory)
@@ -363,7 +364,7 @@ struct RowStudentPow {  // Student-t: W = rowfac * A1[j] * ( c0 + (y1'[j] - m0)^
     __device__ __forceinline__ double cell(const KernelParams& P, const Smem& S, double a, double b) const {
         const double d = a - m0;
         const double t = fma(d, d, c0);  // >= 1
-        return b * pow_neg_c<DEG>(t, P.powc, S.ptab_s);
+        return b * pow_neg_c<DEG>(t, P.powc, S.ptab_s, P.seed_mask, P.seed_half);
     }
 };
 template <> struct Row<KV_STUDENT_POW5> : RowStudentPow<5> {};

@@ -188,13 +188,17 @@ __device__ __forceinline__ double lds_f64(unsigned shared_addr) {
 // shared-window address of the table (cvta.to.shared, hoisted by the caller): with a generic pointer ptxas rebuilds
 // the address from two loop-invariant halves for every lookup.
 template <int DEG>
-__device__ __forceinline__ double pow_neg_c(double t, const double* __restrict__ kc, unsigned tab_s) {
+__device__ __forceinline__ double pow_neg_c(double t, const double* __restrict__ kc, unsigned tab_s, unsigned seed_mask,
+                                            unsigned seed_half) {
     const unsigned hi = (unsigned)__double2hiint(t);
     const unsigned mb = hi & (unsigned)((POW_MTAB - 1) << (20 - POW_BITS));   // interval index, still in place
     const unsigned eb = hi & 0x7ff00000u;                                     // biased exponent, still at bit 20
-    double r;  // == seed_recip(idx, POW_BITS)
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(__hiloint2double((int)(mb | 0x3ff00000u | (1u << (19 - POW_BITS))), 0)));
-    r = __hiloint2double(__double2hiint(r) - (int)eb + 0x3ff00000, 0);        // r_i * 2^-e
+    // MUFU.RCP64H reads the high word only and is exponent-transparent (rcp(2^e m) == 2^-e rcp(m) bit for bit;
+    // checked for every interval and exponent by tools/mufu_check.cu), so the seed of the interval midpoint WITH
+    // t's exponent is r_i * 2^-e directly
+    // seed_mask / seed_half arrive as kernel parameters (not literals) so that (hi & mask) | half is ONE LOP3
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(__hiloint2double((int)((hi & seed_mask) | seed_half), 0)));
     const double f = fma(t, r, -1.0);
     double p = kc[DEG];
 #pragma unroll
