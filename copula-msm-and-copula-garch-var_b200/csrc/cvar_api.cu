@@ -528,11 +528,12 @@ int cvar_plan_create(const cvar_desc_t* desc, const double* x, const double* dx,
 
     // opt in to the dynamic shared memory this grid needs (for the instantiation this plan uses) and size the CTAs.
     // CTA size (measured on B200, tools/sweep_cta_threads.sh): registers cap an SM at 16 resident warps whatever the
-    // CTA size, so small grids do best with small CTAs (cheaper barriers, more days in flight): 64 threads for
-    // n in [192, 640]; tiny grids (n < 192, typically one wave of CTAs) prefer 128 threads for their axis stage;
-    // from there 256 threads while two CTAs fit an SM's shared memory, 512 when only one does.
+    // CTA size, and the more independent CTAs share those warps the better their barrier phases interleave.  So: the
+    // smallest of 64 / 128 / 256 / 512 threads whose resident CTAs (shared memory, registers) still add up to 16 warps
+    // -- 64 threads up to n = 512, 128 up to n ~ 1150, 256 up to n ~ 2300, 512 above (one CTA per SM).  Tiny grids
+    // (n < 192, typically one wave of CTAs) prefer 128 threads for their axis stage.
     int occ = 0;
-    p->cta_threads = n < 192 ? 128 : n <= 640 ? 64 : CTA_THREADS_SMALL;
+    p->cta_threads = n < 192 ? 128 : 0;   // 0: chosen below from the occupancy of this kernel instantiation
     if (const char* env = std::getenv("CVAR_CTA_THREADS")) {   // tuning knob: 32..512, multiple of 32
         const int v = std::atoi(env);
         if (v >= 32 && v <= CTA_THREADS_LARGE && v % 32 == 0) {
@@ -549,11 +550,16 @@ int cvar_plan_create(const cvar_desc_t* desc, const double* x, const double* dx,
         PLAN_TRY((cudaError_t)set_smem(solve_kernel<KV, false>, p->smem_bytes));                                   \
         PLAN_TRY((cudaError_t)set_smem(solve_kernel<KV, true>, p->smem_bytes));                                    \
         PLAN_TRY((cudaError_t)set_smem(strip_mass_kernel<KV>, p->smem_bytes));                                     \
-        for (int attempt = 0; attempt < 2; ++attempt) {                                                            \
-            PLAN_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, solve_kernel<KV, false>, p->cta_threads, p->smem_bytes)); \
-            if (occ >= 2 || attempt == 1) break;                                                                   \
-            p->cta_threads = CTA_THREADS_LARGE; /* only one CTA fits an SM: give it 16 warps */                    \
+        if (p->cta_threads == 0) {                                                                                 \
+            int best_threads = 0, best_resident = -1;                                                              \
+            for (int th = 64; th <= CTA_THREADS_LARGE; th *= 2) {                                                  \
+                PLAN_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, solve_kernel<KV, false>, th, p->smem_bytes)); \
+                const int resident = std::min(occ * th, 512);                                                      \
+                if (resident > best_resident) { best_resident = resident; best_threads = th; }                     \
+            }                                                                                                      \
+            p->cta_threads = best_threads;                                                                         \
         }                                                                                                          \
+        PLAN_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, solve_kernel<KV, false>, p->cta_threads, p->smem_bytes)); \
         break;
     switch (p->kernel_variant) {
         CVAR_PREP(0) CVAR_PREP(1) CVAR_PREP(2) CVAR_PREP(3) CVAR_PREP(4) CVAR_PREP(5) CVAR_PREP(6)

@@ -97,11 +97,15 @@ def test_4096_grid_uses_the_512_thread_layout_and_agrees_with_the_oracle(backend
         assert res.var[k].tobytes() == tr.var.tobytes()
 
 
-def test_small_grids_use_small_ctas(backend):
+def test_cta_size_is_the_smallest_that_keeps_16_warps_resident(backend):
+    """64 / 128 / 256 / 512 threads: the smallest CTA whose resident copies still add up to 16 warps per SM (more
+    independent CTAs interleave their barrier phases better); tiny grids keep 128 threads for the axis stage."""
     from cvar_b200.inputs import make_inputs
-    for n, threads in ((100, 128), (256, 64), (600, 64), (1024, 256), (2048, 256)):
+    for n, threads in ((100, 128), (256, 64), (512, 64), (640, 128), (1024, 128), (1536, 256), (2048, 256)):
         with backend.VarPlan(make_inputs("gaussian", "single", n, sigma=np.ones((1, 2)))) as plan:
-            assert plan.info().threads_per_cta == threads
+            info = plan.info()
+            assert info.threads_per_cta == threads
+            assert n < 192 or info.threads_per_cta * info.ctas_per_sm >= 512
 
 
 def test_mass_is_monotone_in_the_quantile(backend):
