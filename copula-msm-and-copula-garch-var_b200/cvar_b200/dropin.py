@@ -46,23 +46,32 @@ def inputs_from_reference_object(v) -> HotPathInputs:
     return HotPathInputs(**kw)
 
 
-def _plan_for(v, first_guess, second_guess) -> VarPlan:
+def _plan_for(v, inp: HotPathInputs, first_guess, second_guess) -> VarPlan:
+    """One plan per set of run constants: a refit that changes the copula parameters, the grid, the weights or the
+    vol levels of the object gets a new plan instead of a stale cached one."""
     cache = v.__dict__.setdefault("_cvar_b200_plans", {})
-    key = (float(first_guess), float(second_guess[0]), float(second_guess[1]))
+    states = b"" if inp.sigma_states is None else np.ascontiguousarray(inp.sigma_states, dtype=float).tobytes()
+    key = (float(first_guess), float(second_guess[0]), float(second_guess[1]), inp.copula, inp.marginal, int(inp.n),
+           *(None if np.isnan(p) else float(p) for p in (inp.rho, inp.nu, inp.theta)),   # unused parameters are NaN
+           tuple(float(w) for w in inp.weights),
+           np.ascontiguousarray(inp.x, dtype=float).tobytes(), np.ascontiguousarray(inp.dx, dtype=float).tobytes(), states)
     if key not in cache:
-        cache[key] = VarPlan(inputs_from_reference_object(v), first_guess=key[0], second_guess=key[1:])
+        for stale in cache.values():
+            stale.close()
+        cache.clear()
+        cache[key] = VarPlan(inp, first_guess=key[0], second_guess=key[1:3])
     return cache[key]
 
 
 def calc_var(self, obj_var=0.05, first_guess=-3, second_guess=(-3.5, -2)):
     inp = inputs_from_reference_object(self)
-    res = _plan_for(self, first_guess, second_guess).solve(inp.day_params(), [obj_var], ptf_mean=self.ptf_mean)
+    res = _plan_for(self, inp, first_guess, second_guess).solve(inp.day_params(), [obj_var], ptf_mean=self.ptf_mean)
     return res.var[0]
 
 
 def compute_integral(self, bounds):
     inp = inputs_from_reference_object(self)
-    return _plan_for(self, -3, (-3.5, -2)).strip_mass(inp.day_params(), np.asarray(bounds, float))
+    return _plan_for(self, inp, -3, (-3.5, -2)).strip_mass(inp.day_params(), np.asarray(bounds, float))
 
 
 def install(cls):

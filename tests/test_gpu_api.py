@@ -93,6 +93,15 @@ def test_dropin_patches_a_reference_shaped_object(gpu):
         for a in g["alphas"]:
             assert v.calc_var(obj_var=float(a)).tobytes() == g[f"ref_var_{a}"].tobytes()
         np.testing.assert_allclose(v.compute_integral(g["bounds"]), g["ref_strip_mass"], rtol=0, atol=2e-13)
+        # one cached plan for all of the above; a refit of the copula parameters must not reuse it
+        assert len(v._cvar_b200_plans) == 1
+        first = next(iter(v._cvar_b200_plans.values()))
+        before = v.calc_var(obj_var=0.05)
+        assert next(iter(v._cvar_b200_plans.values())) is first
+        v.copula_params = np.array([inp.nu + 3.0, 0.1])
+        after = v.calc_var(obj_var=0.05)
+        assert len(v._cvar_b200_plans) == 1 and next(iter(v._cvar_b200_plans.values())) is not first
+        assert not np.array_equal(before, after)
     finally:
         dropin.uninstall(ValueAtRiskCalcualtion)
 
