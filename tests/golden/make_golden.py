@@ -137,6 +137,16 @@ def build_cases():
     add("gaussian_garch_n1024_T2", "gaussian", "single", 1024, sigma=syn.garch_sigma_path(2), alphas=(0.01,), strips=False)
     add("student_msm8_n96_T2", "student", "mixture", 96, vs_probs=_msm8(2), alphas=(0.01, 0.05))
     add("plackett_msm8_n96_w64", "plackett", "mixture", 96, vs_probs=_msm8(2), weights=(0.6, 0.4), alphas=(0.01,))
+    # --- round-1 additions: odd / tiny grids, extreme parameters on the mixture path, other alphas -----------------
+    add("x_student_msm8_rho-0.5_w37_n56", "student", "mixture", 56, vs_probs=vp8, weights=(0.3, 0.7), rho=-0.5, nu=3.2,
+        alphas=(0.01, 0.05))
+    add("x_gaussian_msm8_rho-0.7_n60", "gaussian", "mixture", 60, vs_probs=vp8, rho=-0.7, alphas=(0.05,))
+    add("x_plackett_kat1mix_theta0.5_n52", "plackett", "mixture", 52, vs_probs=_kat1_mixture(), theta=0.5, alphas=(0.01, 0.05))
+    add("x_student_nu2.01_n64", "student", "single", 64, sigma=sig_kat1, nu=2.01, rho=0.3, alphas=(0.01,))
+    add("x_student_nu50_n64", "student", "single", 64, sigma=sig_kat1, nu=50.0, rho=0.8, alphas=(0.05,))
+    add("x_gaussian_odd_n101", "gaussian", "single", 101, sigma=sig_kat2, alphas=(0.01, 0.1))
+    add("x_plackett_tiny_n37", "plackett", "single", 37, sigma=sig_kat1, alphas=(0.05, 0.2), theta=9.0)
+    add("x_student_garch_alpha0.001_n72", "student", "single", 72, sigma=syn.garch_sigma_path(6), alphas=(0.001, 0.25))
     return cases
 
 
