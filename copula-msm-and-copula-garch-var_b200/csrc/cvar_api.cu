@@ -405,6 +405,12 @@ int cvar_plan_create(const cvar_desc_t* desc, const double* x, const double* dx,
     kp.compat = desc->compat_flags;
     kp.rho = desc->rho; kp.nu = desc->nu; kp.theta = desc->theta;
     kp.w0 = desc->w0; kp.w1 = desc->w1;
+    {
+        int ex = 0;
+        const double mant = std::frexp(std::fabs(desc->w0), &ex);
+        // exact for every finite numerator unless the quotient leaves the normal range, which |q|, |x| <= 100 exclude
+        kp.rw0_exact = (mant == 0.5 && ex > -500 && ex < 500) ? 1.0 / desc->w0 : 0.0;
+    }
     kp.neg_inf = desc->neg_inf; kp.first = desc->first_guess;
     kp.second_lo = desc->second_lo; kp.second_hi = desc->second_hi;
     kp.min_var = desc->min_var; kp.max_var = desc->max_var;

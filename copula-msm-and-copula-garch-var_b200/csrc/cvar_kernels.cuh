@@ -64,6 +64,7 @@ struct KernelParams {
     int max_iter;
     int cmin;  // #{x <= clip_lo}: first inner index that can ever belong to a strip
     double rho, nu, theta, w0, w1;
+    double rw0_exact;  // 1 / w0 when w0 is a power of two (division == multiplication, exactly), else 0
     double neg_inf, first, second_lo, second_hi, min_var, max_var;
     // copula constants prepared on the host
     double g_in_scale;   // gaussian: sqrt(kappa*log2e)          student: 1/sqrt(nu(1-rho^2))
@@ -260,9 +261,12 @@ __global__ void state_table_kernel(int n, int q, const double* __restrict__ x, c
 // ---------------------------------------------------------------------------------------------
 // membership: #{ j : x[j] <= g } by binary search inside [lo, hi]
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ double inner_bound(double q, double xi, double w0, double w1) {
-    // (q - x_outer * w[1]) / w[0], every operation individually rounded (integration_algo.py:20)
-    return __ddiv_rn(__dsub_rn(q, __dmul_rn(xi, w1)), w0);
+__device__ __forceinline__ double inner_bound(double q, double xi, double w0, double w1, double rw0_exact) {
+    // (q - x_outer * w[1]) / w[0], every operation individually rounded (integration_algo.py:20).  When w[0] is a
+    // power of two (the reference's default 0.5) the division equals the multiplication by its exact reciprocal bit
+    // for bit, which spares the ~20-instruction IEEE division per row and strip; rw0_exact is 0 otherwise.
+    const double num = __dsub_rn(q, __dmul_rn(xi, w1));
+    return rw0_exact != 0.0 ? __dmul_rn(num, rw0_exact) : __ddiv_rn(num, w0);
 }
 
 __device__ __forceinline__ int count_le(const double* __restrict__ xs, double g, int lo, int hi) {
@@ -302,7 +306,7 @@ __device__ __forceinline__ int owned_rounds(const Part& pt, int n) {
 
 // c = max(#{x <= g_i(q)}, cmin) for outer row i; the search is confined to [lo, hi]
 __device__ __forceinline__ int count_row(const KernelParams& P, const Smem& S, double q, int i, int lo, int hi) {
-    const double g = inner_bound(q, S.xs[i], P.w0, P.w1);
+    const double g = inner_bound(q, S.xs[i], P.w0, P.w1, P.rw0_exact);
     if (lo > 0 && !(S.xs[lo - 1] <= g)) lo = 0;  // stored bounds are clipped at cmin; stay exact
     return max(count_le(S.xs, g, lo, hi), P.cmin);
 }
