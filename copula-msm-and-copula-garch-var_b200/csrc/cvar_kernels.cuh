@@ -378,21 +378,23 @@ template <> struct Row<KV_STUDENT_POW8> : RowStudentPow<8> {};
 
 template <>
 struct Row<2> {  // Plackett (the reference's formula, plackett.py:66-69), u = row, v = column
-    double n0, n1, p0, r0, eta, fac;
+    double n0, n1, qa, qb, qc, fac;
     __device__ __forceinline__ void load(const KernelParams& P, const Smem& S, int i) {
         const double u = S.out0[i];
-        eta = P.theta - 1.0;
-        p0 = 1.0 + eta * u;
-        r0 = 1.0 + eta * (1.0 - u);
+        const double eta = P.theta - 1.0;
+        const double p0 = 1.0 + eta * u;
+        const double r0 = 1.0 + eta * (1.0 - u);
         n0 = P.theta * p0;
         n1 = P.theta * eta * (1.0 - 2.0 * u);
+        // (p0 + eta v)(r0 - eta v) as one quadratic in v: two FMAs per cell instead of two FMAs and a multiply
+        qa = -eta * eta;
+        qb = eta * (r0 - p0);
+        qc = p0 * r0;
         fac = S.out1[i];
     }
     __device__ __forceinline__ double cell(const KernelParams&, const Smem&, double v, double a1) const {
         const double num = fma(n1, v, n0);
-        const double pp = fma(eta, v, p0);
-        const double rr = fma(-eta, v, r0);
-        const double dd = pp * rr;
+        const double dd = fma(v, fma(v, qa, qb), qc);
         return (a1 * num) * rcp_cell(dd * dd);
     }
 };
