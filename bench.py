@@ -34,13 +34,13 @@ METRIC = "VaR solves/sec (day x alpha)"
 UNIT = "solves/s"
 DEFAULT_WORKLOAD = "c3"
 # dram__bytes_read.sum + dram__bytes_write.sum of one solve_kernel launch, from the committed ncu --set full captures
-# (profiles/r1_c3_solve_kernel_v10_ncu_summary.txt, profiles/r1_c4_solve_kernel_v8_ncu_summary.txt); the kernel
+# (profiles/r1_c3_solve_kernel_v12_ncu_summary.txt, profiles/r1_c4_solve_kernel_v12_ncu_summary.txt); the kernel
 # reads 144 KB (c3) / 16 KB (c4) of per-day parameters plus the plan tables (c3: 0.6 MB of mixture state tables, mostly
 # L2 hits) and writes 8-16 KB of decision words that stay in L2.
-NCU_DRAM_BYTES_PER_LAUNCH = {"c3": 888576, "c4": 139520}
+NCU_DRAM_BYTES_PER_LAUNCH = {"c3": 889856, "c4": 140032}
 # sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active from the same captures: the ISSUED-instruction view of
 # the FP64 pipe, next to the algorithmic-flop fraction (which can exceed 1)
-NCU_FP64_PIPE_PCT = {"c3": 51.1, "c4": 53.8}
+NCU_FP64_PIPE_PCT = {"c3": 51.9, "c4": 50.0}
 WORKLOAD_DESCRIPTIONS = {
     "c1": "BASELINE configs[0]: Gaussian copula + GARCH(1,1) sigma path, n=100, 99% VaR",
     "c2": "BASELINE configs[1]: Student-t copula + GARCH(1,1), n=1024, 95%/99% VaR",
