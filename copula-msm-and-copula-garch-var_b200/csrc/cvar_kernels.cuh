@@ -488,6 +488,9 @@ __device__ StripResult strip_pass(const KernelParams& P, const Smem& S, const Pa
         }
         int s = ca ? (int)ca[i] : P.cmin;
         int e = (int)cb[i];
+#ifdef CVAR_DEBUG_ASSERT
+        if (s < 0 || e > n || (do_count && (int)cnew[i] > n)) __trap();
+#endif
         if (e <= s) continue;
         cells += (unsigned)(e - s);
         if (i < L.i_lo || i >= L.i_hi) {

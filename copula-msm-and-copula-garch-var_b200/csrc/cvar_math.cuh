@@ -193,6 +193,9 @@ __device__ __forceinline__ double pow_neg_c(double t, const double* __restrict__
     const unsigned hi = (unsigned)__double2hiint(t);
     const unsigned mb = hi & (unsigned)((POW_MTAB - 1) << (20 - POW_BITS));   // interval index, still in place
     const unsigned eb = hi & 0x7ff00000u;                                     // biased exponent, still at bit 20
+#ifdef CVAR_DEBUG_ASSERT
+    if (!(t >= 1.0) || (eb >> 20) < 1023u || (eb >> 20) >= 1023u + POW_ETAB) __trap();   // table range (see y_max)
+#endif
     // MUFU.RCP64H reads the high word only and is exponent-transparent (rcp(2^e m) == 2^-e rcp(m) bit for bit;
     // checked for every interval and exponent by tools/mufu_check.cu), so the seed of the interval midpoint WITH
     // t's exponent is r_i * 2^-e directly
