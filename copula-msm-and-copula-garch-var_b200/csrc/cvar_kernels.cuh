@@ -291,7 +291,12 @@ __device__ __forceinline__ int count_le(const double* __restrict__ xs, double g,
 // through distributed shared memory (block_reduce).
 struct Part {
     int rank, size;  // this CTA's rank in the cluster and the cluster size (0, 1 without a cluster)
+    int rounds;      // rows per thread: ceil(n / (size * blockDim.x)), computed once (an integer division)
 };
+__device__ __forceinline__ Part make_part(int rank, int size, int n) {
+    const int per = size * (int)blockDim.x;
+    return Part{rank, size, (n + per - 1) / per};
+}
 
 __device__ __forceinline__ int owned_row(const Part& pt, int m) {
     const int w = pt.rank * (blockDim.x >> 5) + (threadIdx.x >> 5), l = threadIdx.x & 31;
@@ -299,10 +304,7 @@ __device__ __forceinline__ int owned_row(const Part& pt, int m) {
     const int wb = (m & 1) ? (nw - 1 - w) : w;
     return ((m * nw + wb) << 5) + l;
 }
-__device__ __forceinline__ int owned_rounds(const Part& pt, int n) {
-    const int per = pt.size * blockDim.x;
-    return (n + per - 1) / per;
-}
+__device__ __forceinline__ int owned_rounds(const Part& pt, int) { return pt.rounds; }
 
 // c = max(#{x <= g_i(q)}, cmin) for outer row i; the search is confined to [lo, hi]
 __device__ __forceinline__ int count_row(const KernelParams& P, const Smem& S, double q, int i, int lo, int hi) {
@@ -573,11 +575,10 @@ solve_kernel(KernelParams P, const double* __restrict__ day_params, long long T,
              unsigned long long* __restrict__ cells_out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const Smem S = carve(smem_raw, P.n, COPULA);
-    Part pt = {0, 1};
+    Part pt = make_part(0, 1, P.n);
     if (CLUSTER) {
         cooperative_groups::cluster_group cluster = cooperative_groups::this_cluster();
-        pt.rank = (int)cluster.block_rank();
-        pt.size = (int)cluster.num_blocks();
+        pt = make_part((int)cluster.block_rank(), (int)cluster.num_blocks(), P.n);
     }
     // CTAs are dispatched in block-index order; `order` lists the days most expensive first (see order_key_kernel)
     const long long unit = blockIdx.x / pt.size;
@@ -696,7 +697,7 @@ strip_mass_kernel(KernelParams P, const double* __restrict__ day_params, const d
     const bool poison_mode = (COPULA != 2) && (P.marginal == 1) && ((P.compat & 4u) != 0);
     int parity = 0;
     const double lo = bounds[2 * day], hi = bounds[2 * day + 1];
-    const Part pt = {0, 1};
+    const Part pt = make_part(0, 1, P.n);
     count_rows(P, S, pt, lo, S.c[0], nullptr, nullptr);
     // an inverted pair yields an empty strip (cb <= ca), like the reference's empty np.where
     const StripResult s = strip_pass<COPULA>(P, S, pt, L, parity, true, hi, S.c[1], nullptr, nullptr, S.c[0], S.c[1], poison_mode);
