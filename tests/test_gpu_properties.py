@@ -192,3 +192,19 @@ def test_cluster_split_days_equal_single_cta_days(backend, monkeypatch, cuda_dev
         assert got[3].tobytes() == single[3].tobytes()
         np.testing.assert_allclose(got[1], single[1], rtol=1e-13, atol=1e-18)
     assert auto[1].tobytes() == forced[1].tobytes()          # the automatic choice is the expected cluster size
+
+
+def test_batches_below_the_sm_count_agree_with_the_oracle(backend):
+    """75..#SMs days of an n >= 1024 grid launch one 512-thread CTA per day (no cluster): spot-check against the oracle
+    and against the same days solved inside a large batch (256-thread CTAs)."""
+    from oracle import var_oracle as vo
+    inp, _ = _inputs("c2", 1024, 300)
+    small = inp.take_days(slice(0, 100))
+    with backend.VarPlan(inp) as plan:
+        big = plan.solve(inp.day_params(), [0.01], forced_iterations=22)
+        few = plan.solve(small.day_params(), [0.01], forced_iterations=22)
+    assert few.var.tobytes() == big.var[:, :100].tobytes() and np.array_equal(few.case, big.case[:, :100])
+    assert np.array_equal(few.cells, big.cells[:, :100])
+    days = [0, 57, 99]
+    tr = vo.calc_var(small, 0.01, days=days, forced_iterations=22)
+    assert few.var[0, days].tobytes() == tr.var.tobytes()
