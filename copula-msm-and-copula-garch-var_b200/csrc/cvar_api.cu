@@ -415,6 +415,25 @@ int cvar_plan_create(const cvar_desc_t* desc, const double* x, const double* dx,
     kp.second_lo = desc->second_lo; kp.second_hi = desc->second_hi;
     kp.min_var = desc->min_var; kp.max_var = desc->max_var;
     kp.cmin = (int)(std::upper_bound(x, x + n, desc->clip_lo) - x);
+    {   // uniform segments of the axis, for the boundary guess (cvar_kernels.cuh, count_row)
+        std::vector<int> first{0};
+        for (int i = 2; i < n; ++i) {
+            const double h0 = x[i - 1] - x[i - 2], h1 = x[i] - x[i - 1];
+            if (std::fabs(h1 - h0) > 1e-6 * std::fabs(h0)) first.push_back(i - 1);   // spacing changes at x[i-1]
+        }
+        kp.nseg = 0;
+        for (int s = 0; s < MAX_AXIS_SEGMENTS; ++s) kp.seg_x0[s] = INFINITY, kp.seg_inv_h[s] = 0.0, kp.seg_first[s] = n;
+        kp.seg_first[MAX_AXIS_SEGMENTS] = n;
+        if ((int)first.size() <= MAX_AXIS_SEGMENTS && std::getenv("CVAR_NO_SEGMENT_GUESS") == nullptr) {
+            kp.nseg = (int)first.size();
+            for (int s = 0; s < kp.nseg; ++s) {
+                const int a = first[s], b = (s + 1 < kp.nseg) ? first[s + 1] : n - 1;   // segment spans x[a] .. x[b]
+                kp.seg_first[s] = a;
+                kp.seg_x0[s] = x[a];
+                kp.seg_inv_h[s] = b > a ? (double)(b - a) / (x[b] - x[a]) : 0.0;
+            }
+        }
+    }
     double dx_min = INFINITY;
     for (int i = 1; i < n; ++i) dx_min = std::min(dx_min, x[i] - x[i - 1]);
     const double LOG2E = 1.4426950408889634;

@@ -58,6 +58,8 @@ typedef unsigned short u16;
 constexpr int MEMO_SIZE = 32;
 constexpr int MEMO_PER_ALPHA = 7;
 
+constexpr int MAX_AXIS_SEGMENTS = 8;
+
 struct KernelParams {
     int copula, marginal, n, q;
     unsigned compat;
@@ -65,6 +67,11 @@ struct KernelParams {
     int cmin;  // #{x <= clip_lo}: first inner index that can ever belong to a strip
     double rho, nu, theta, w0, w1;
     double rw0_exact;  // 1 / w0 when w0 is a power of two (division == multiplication, exactly), else 0
+    // uniform segments of the axis (the reference's axis has five); nseg = 0: not piecewise uniform, plain bisection
+    int nseg;
+    int seg_first[MAX_AXIS_SEGMENTS + 1];     // first index of segment s; seg_first[nseg] = n
+    double seg_x0[MAX_AXIS_SEGMENTS];         // x[seg_first[s]]; +inf beyond nseg
+    double seg_inv_h[MAX_AXIS_SEGMENTS];      // 1 / spacing of segment s
     double neg_inf, first, second_lo, second_hi, min_var, max_var;
     // copula constants prepared on the host
     double g_in_scale;   // gaussian: sqrt(kappa*log2e)          student: 1/sqrt(nu(1-rho^2))
@@ -310,7 +317,24 @@ __device__ __forceinline__ int owned_rounds(const Part& pt, int) { return pt.rou
 __device__ __forceinline__ int count_row(const KernelParams& P, const Smem& S, double q, int i, int lo, int hi) {
     const double g = inner_bound(q, S.xs[i], P.w0, P.w1, P.rw0_exact);
     if (lo > 0 && !(S.xs[lo - 1] <= g)) lo = 0;  // stored bounds are clipped at cmin; stay exact
-    return max(count_le(S.xs, g, lo, hi), P.cmin);
+    int k;
+    if (P.nseg > 0 && hi - lo > 4) {
+        // Piecewise-uniform axis: the count is known to +-1 from the segment's spacing, and the two comparisons that
+        // settle it replace a chain of log2(hi - lo) dependent shared-memory loads.  The result is still decided by
+        // comparisons with the axis values themselves, so it is exact whatever the quality of the guess.
+        int sgm = 0;
+#pragma unroll
+        for (int t = 1; t < MAX_AXIS_SEGMENTS; ++t) sgm += (g >= P.seg_x0[t]) ? 1 : 0;
+        const int first = P.seg_first[sgm], next = P.seg_first[sgm + 1];
+        k = first + __double2int_rd((g - P.seg_x0[sgm]) * P.seg_inv_h[sgm]) + 1;
+        k = min(max(k, first), next);
+        k = min(max(k, lo), hi);
+        while (k > lo && !(S.xs[k - 1] <= g)) --k;
+        while (k < hi && S.xs[k] <= g) ++k;
+    } else {
+        k = count_le(S.xs, g, lo, hi);
+    }
+    return max(k, P.cmin);
 }
 
 // ctarget[i] = count_row(q) for every outer row this thread owns

@@ -138,6 +138,7 @@ typedef struct cvar_plan_info {
  *   CVAR_CLUSTER=1|2|4         fixed number of CTAs (thread-block cluster) per day; default: 4 / 2 while the whole batch
  *                              stays resident (n >= 1024), else 1
  *   CVAR_STUDENT_GENERIC=1     Student-t plans use the generic log2/exp2 cell instead of the table-assisted power cell
+ *   CVAR_NO_SEGMENT_GUESS=1    row boundaries by plain bisection even on a piecewise-uniform axis
  * The Python loader additionally honours CVAR_B200_LIB=<path to an alternative libcvar_b200.so>.
  */
 
