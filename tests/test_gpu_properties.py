@@ -208,3 +208,42 @@ def test_batches_below_the_sm_count_agree_with_the_oracle(backend):
     days = [0, 57, 99]
     tr = vo.calc_var(small, 0.01, days=days, forced_iterations=22)
     assert few.var[0, days].tobytes() == tr.var.tobytes()
+
+
+@pytest.mark.parametrize("axis", ["sinh", "two_segments", "nine_segments", "jittered"])
+def test_row_boundaries_stay_exact_on_any_axis(backend, axis):
+    """The boundary guess uses the uniform segments of the axis (<= 8, found at plan creation); other axes fall back to
+    bisection, and a guess that is off (jittered spacing inside a 'segment') is corrected by the exact comparisons.
+    Cell counts and VaR must equal the oracle's on every kind of axis."""
+    import dataclasses
+    from oracle import var_oracle as vo
+    from cvar_b200.inputs import make_inputs
+    n = 120
+    rng = np.random.default_rng(11)
+    if axis == "sinh":
+        x = 5.0 * np.sinh(np.linspace(-2.0, 2.0, n)) / np.sinh(2.0)
+    elif axis == "two_segments":
+        x = np.concatenate([np.linspace(-5.0, -1.0, 40, endpoint=False), np.linspace(-1.0, 5.0, n - 40)])
+    elif axis == "nine_segments":
+        edges = np.linspace(-5.0, 5.0, 10)
+        counts = [10, 16, 12, 14, 13, 15, 11, 17]
+        parts = [np.linspace(edges[k], edges[k + 1], c, endpoint=False) for k, c in enumerate(counts)]
+        parts.append(np.linspace(edges[8], edges[9], n - sum(counts)))
+        x = np.concatenate(parts)
+    else:   # spacing equal to 1e-7 relative (below the detection threshold) ... except where it is not
+        x = np.linspace(-5.0, 5.0, n)
+        x[1:-1] += rng.uniform(-2e-8, 2e-8, n - 2)
+    assert np.all(np.diff(x) > 0) and len(x) == n
+    dx = np.diff(x, prepend=x[0]); dx[0] = dx[1]
+    base = make_inputs("gaussian", "single", n, rho=0.5, sigma=np.array([[0.8, 1.1], [1.5, 1.2], [2.6, 2.2]]), weights=(0.4, 0.6))
+    inp = dataclasses.replace(base, x=x, dx=dx)
+    bounds = np.array([[-100.0, -2.2], [-3.1, -0.4], [-1.0, 0.3]])
+    with backend.VarPlan(inp) as plan:
+        mass, cells = plan.strip_mass(inp.day_params(), bounds, return_cells=True)
+        res = plan.solve(inp.day_params(), [0.01, 0.05])
+    np.testing.assert_allclose(mass, vo.compute_integral(inp, bounds), rtol=2e-12, atol=2e-13)
+    want_cells = [int(np.sum(np.subtract(*vo.strip_ranges(inp, lo, hi)[::-1]))) for lo, hi in bounds]
+    assert np.array_equal(cells, np.array(want_cells, dtype=np.uint64))
+    for k, a in enumerate([0.01, 0.05]):
+        tr = vo.calc_var(inp, a)
+        assert res.var[k].tobytes() == tr.var.tobytes() and np.array_equal(res.case[k], tr.case)
