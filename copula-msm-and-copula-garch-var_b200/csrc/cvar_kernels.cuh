@@ -316,7 +316,10 @@ __device__ __forceinline__ int owned_rounds(const Part& pt, int) { return pt.rou
 // c = max(#{x <= g_i(q)}, cmin) for outer row i; the search is confined to [lo, hi]
 __device__ __forceinline__ int count_row(const KernelParams& P, const Smem& S, double q, int i, int lo, int hi) {
     const double g = inner_bound(q, S.xs[i], P.w0, P.w1, P.rw0_exact);
-    if (lo > 0 && !(S.xs[lo - 1] <= g)) lo = 0;  // stored bounds are clipped at cmin; stay exact
+    // Stored bounds are counts at a smaller q, clipped at cmin.  With w0 > 0 the bound grows with q, so the count
+    // sought is >= the stored one or both lie below cmin (and the result is clipped to cmin either way): [lo, hi]
+    // always contains the answer.  Only a negative w0 reverses the order, and then the bracket is re-opened.
+    if (P.w0 < 0.0 && lo > 0 && !(S.xs[lo - 1] <= g)) lo = 0;
     int k;
     if (P.nseg > 0 && hi - lo > 4) {
         // Piecewise-uniform axis: the count is known to +-1 from the segment's spacing, and the two comparisons that
