@@ -1,6 +1,7 @@
 // cvar_kernels.cuh -- the per-day VaR solve on sm_100a.
 //
-// One CTA per out-of-sample day.  The CTA
+// One CTA per out-of-sample day (a 2- or 4-CTA thread-block cluster per day when the batch is smaller than the
+// GPU, see solve_kernel).  The CTA
 //   stage 0  evaluates every per-axis-point quantity once (marginal cdf/pdf, the MSM mixture over its
 //            q states, the copula quantile) and leaves them in shared memory in the form the cell loop
 //            wants (reference: integration_functions/*_integration_function.py,
@@ -21,13 +22,13 @@
 
 namespace cvar {
 
-// CTA size is chosen per plan: 256 threads when two CTAs fit one SM's shared memory (n <= ~2300), otherwise
-// one CTA of 512 threads per SM, so that an SM always has 16 warps of row walkers resident.
+// CTA size is chosen per plan (cvar_api.cu): the smallest of 64 / 128 / 256 / 512 threads whose resident copies
+// still give an SM 16 warps of row walkers; 512 threads when only one CTA fits an SM or the batch is small.
 constexpr int CTA_THREADS_SMALL = 256;
 constexpr int CTA_THREADS_LARGE = 512;
 constexpr int MAX_CTA_WARPS = CTA_THREADS_LARGE / 32;
-// Kernel variants (template parameter COPULA of the kernels below): the three copula families plus three
-// Student-t variants whose cell uses the table-assisted power with a binomial series of fixed degree.
+// Kernel variants (template parameter COPULA of the kernels below): the three copula families plus four
+// Student-t variants whose cell uses the table-assisted power with a plan-fitted polynomial of fixed degree.
 constexpr int KV_GAUSSIAN = 0, KV_STUDENT = 1, KV_PLACKETT = 2, KV_STUDENT_POW5 = 3, KV_STUDENT_POW6 = 4, KV_STUDENT_POW7 = 5,
               KV_STUDENT_POW8 = 6, KV_COUNT = 7;
 __host__ __device__ constexpr bool kv_is_student(int kv) { return kv == KV_STUDENT || kv >= KV_STUDENT_POW5; }

@@ -113,7 +113,7 @@ __device__ __forceinline__ double log2_fast(double t) {
 }
 
 // ----- table-assisted  c * log2(t)  for the Student-t cell -----------------------------------------
-// t = 2^e * m, m in [1, 2).  The top 7 mantissa bits select an interval; its midpoint reciprocal r_i comes
+// t = 2^e * m, m in [1, 2).  The top LOGTAB_BITS (7) mantissa bits select an interval; its midpoint reciprocal r_i comes
 // from MUFU.RCP64H (deterministic, so the table built with the same instruction matches it exactly) and
 // f = m * r_i - 1 is exact in one DFMA with |f| <= 2^-8.  Then
 //     c * log2(t) = c * e + c * (-log2 r_i) + f * (c * Q(f)),   Q(f) = log2(1+f)/f  (degree 5)
