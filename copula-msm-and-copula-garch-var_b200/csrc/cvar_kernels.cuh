@@ -398,7 +398,7 @@ struct RowStudentPow {  // Student-t: W = rowfac * A1[j] * ( c0 + (y1'[j] - m0)^
     __device__ __forceinline__ double cell(const KernelParams& P, const Smem& S, double a, double b) const {
         const double d = a - m0;
         const double t = fma(d, d, c0);  // >= 1
-        return b * pow_neg_c<DEG>(t, P.powc, S.ptab_s, P.seed_mask, P.seed_half);
+        return pow_neg_c<DEG>(t, b, P.powc, S.ptab_s, P.seed_mask, P.seed_half);
     }
 };
 template <> struct Row<KV_STUDENT_POW5> : RowStudentPow<5> {};

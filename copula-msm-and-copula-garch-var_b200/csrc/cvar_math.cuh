@@ -187,9 +187,11 @@ __device__ __forceinline__ double lds_f64(unsigned shared_addr) {
 // and exponent fields of t's high word are shifted straight into byte offsets, one integer op each.  `tab_s` is the
 // shared-window address of the table (cvta.to.shared, hoisted by the caller): with a generic pointer ptxas rebuilds
 // the address from two loop-invariant halves for every lookup.
+// Returns b * t^(-c); the caller's column weight b is folded into the table product so that only one FMA of the
+// caller follows the polynomial on the dependency chain.
 template <int DEG>
-__device__ __forceinline__ double pow_neg_c(double t, const double* __restrict__ kc, unsigned tab_s, unsigned seed_mask,
-                                            unsigned seed_half) {
+__device__ __forceinline__ double pow_neg_c(double t, double b, const double* __restrict__ kc, unsigned tab_s,
+                                            unsigned seed_mask, unsigned seed_half) {
     const unsigned hi = (unsigned)__double2hiint(t);
     const unsigned mb = hi & (unsigned)((POW_MTAB - 1) << (20 - POW_BITS));   // interval index, still in place
     const unsigned eb = hi & 0x7ff00000u;                                     // biased exponent, still at bit 20
@@ -208,7 +210,7 @@ __device__ __forceinline__ double pow_neg_c(double t, const double* __restrict__
     for (int k = DEG - 1; k >= 0; --k) p = fma(p, f, kc[k]);
     const double pm = lds_f64(tab_s + (mb >> (20 - POW_BITS - 3)));
     const double pe = lds_f64(tab_s + (unsigned)((POW_MTAB - 1023) * 8) + (eb >> 17));
-    return (pm * pe) * p;
+    return ((pm * pe) * b) * p;
 }
 
 // ---------------------------------------------------------------------------------------------
