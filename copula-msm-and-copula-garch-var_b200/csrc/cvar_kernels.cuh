@@ -368,6 +368,10 @@ struct Row<0> {  // Gaussian:  W = rowfac * 2^( l1[j] - (y1'[j] - m0)^2 )
         const double d = a - m0;
         return exp2_tab(fma(-d, d, b), S.etab);
     }
+    __device__ __forceinline__ double add_cell(const KernelParams&, const Smem& S, double a, double b, double acc) const {
+        const double d = a - m0;
+        return exp2_tab_add(fma(-d, d, b), S.etab, acc);
+    }
 };
 
 template <>
@@ -384,6 +388,11 @@ struct Row<1> {  // Student-t: W = rowfac * 2^( l1[j] - (nu+2)/2 * log2( c0 + (y
         const double t = fma(d, d, c0);  // >= 1
         return exp2_tab(scaled_log2_plus(t, b, P.negc, P.qc, S.ltab), S.etab);
     }
+    __device__ __forceinline__ double add_cell(const KernelParams& P, const Smem& S, double a, double b, double acc) const {
+        const double d = a - m0;
+        const double t = fma(d, d, c0);
+        return exp2_tab_add(scaled_log2_plus(t, b, P.negc, P.qc, S.ltab), S.etab, acc);
+    }
 };
 
 template <int DEG>
@@ -399,6 +408,9 @@ struct RowStudentPow {  // Student-t: W = rowfac * A1[j] * ( c0 + (y1'[j] - m0)^
         const double d = a - m0;
         const double t = fma(d, d, c0);  // >= 1
         return pow_neg_c<DEG>(t, b, P.powc, S.ptab_s, P.seed_mask, P.seed_half);
+    }
+    __device__ __forceinline__ double add_cell(const KernelParams& P, const Smem& S, double a, double b, double acc) const {
+        return acc + cell(P, S, a, b);   // contracts to one FMA with the last product of pow_neg_c
     }
 };
 template <> struct Row<KV_STUDENT_POW5> : RowStudentPow<5> {};
@@ -426,6 +438,9 @@ struct Row<2> {  // Plackett (the reference's formula, plackett.py:66-69), u = r
         const double num = fma(n1, v, n0);
         const double dd = fma(v, fma(v, qa, qb), qc);
         return (a1 * num) * rcp_cell(dd * dd);
+    }
+    __device__ __forceinline__ double add_cell(const KernelParams& P, const Smem& S, double v, double a1, double acc) const {
+        return acc + cell(P, S, v, a1);
     }
 };
 
@@ -542,11 +557,11 @@ __device__ StripResult strip_pass(const KernelParams& P, const Smem& S, const Pa
 #pragma unroll
             for (int c = 0; c < CELLS_IN_FLIGHT; ++c) v[c] = S.in[j + c];
 #pragma unroll
-            for (int c = 0; c < CELLS_IN_FLIGHT; ++c) acc[c] += row.cell(P, S, v[c].x, v[c].y);
+            for (int c = 0; c < CELLS_IN_FLIGHT; ++c) acc[c] = row.add_cell(P, S, v[c].x, v[c].y, acc[c]);
         }
         for (; j < e; ++j) {
             const double2 v = S.in[j];
-            acc[0] += row.cell(P, S, v.x, v.y);
+            acc[0] = row.add_cell(P, S, v.x, v.y, acc[0]);
         }
         double rowsum = acc[0];
 #pragma unroll

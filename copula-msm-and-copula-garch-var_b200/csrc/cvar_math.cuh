@@ -71,6 +71,22 @@ __device__ __forceinline__ double exp2_tab(double t, const double* __restrict__ 
     return __hiloint2double(__double2hiint(v) + (k << 20), __double2loint(v));
 }
 
+// acc + 2^t: the table entry takes the exponent first (an integer add, off the dependency chain), so the polynomial is
+// followed by ONE fused multiply-add instead of a multiply, the exponent add and an add.
+__device__ __forceinline__ double exp2_tab_add(double t, const double* __restrict__ tab, double acc) {
+    const double MAGIC = 6755399441055744.0 / EXPTAB_SIZE;
+    const double kf = __dadd_rn(t, MAGIC);
+    const int k256 = __double2loint(kf);
+    const double r = __dadd_rn(t, -__dadd_rn(kf, -MAGIC));
+    double p = kExp2SmallCoef[CVAR_EXP2_TAB_POLY_DEG];
+#pragma unroll
+    for (int i = CVAR_EXP2_TAB_POLY_DEG - 1; i >= 0; --i) p = fma(p, r, kExp2SmallCoef[i]);
+    const double tv = tab[k256 & (EXPTAB_SIZE - 1)];                        // in [1, 2)
+    const int k = max(k256 >> EXPTAB_BITS, -1021);
+    const double ts = __hiloint2double(__double2hiint(tv) + (k << 20), __double2loint(tv));   // 2^k * table entry, normal
+    return fma(ts, p, acc);
+}
+
 // 1/a for finite normal a: MUFU.RCP64H seed (2^-23) + two Newton steps on the FP64 pipe.
 __device__ __forceinline__ double rcp_fast(double a) {
     double r;
