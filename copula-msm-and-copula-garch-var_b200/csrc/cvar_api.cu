@@ -44,6 +44,7 @@ struct cvar_plan {
     double* d_logtab;
     double* d_exptab;
     double* d_powtab;
+    double* d_powfast;
     int kernel_variant;  // KV_* template instantiation used by this plan
     double* d_state_cdf;
     double* d_state_pdf;
@@ -153,6 +154,63 @@ __global__ void tq_table_check_kernel(double nu, const double* __restrict__ tabl
     const double fast = t_quantile_mag_table(table, nu, tail_lc, p);
     const double err = fabs(fast - exact) / fmax(exact, 0.1);  // relative in the tails, absolute (x10) around the median
     atomicMax(max_err_bits, (unsigned long long)__double_as_longlong(err));  // err >= 0: bit order == value order
+}
+
+// Resident CTAs per SM of the solve kernel of variant `kv` at `threads` per CTA and `smem` bytes of dynamic shared memory.
+template <int KV>
+int occupancy_of(int threads, size_t smem, int* occ) {
+    return (int)cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, solve_kernel<KV, false>, threads, smem);
+}
+int solve_occupancy(int kv, int threads, size_t smem, int* occ) {
+    switch (kv) {
+        case 0: return occupancy_of<0>(threads, smem, occ);
+        case 1: return occupancy_of<1>(threads, smem, occ);
+        case 2: return occupancy_of<2>(threads, smem, occ);
+        case 3: return occupancy_of<3>(threads, smem, occ);
+        case 4: return occupancy_of<4>(threads, smem, occ);
+        case 5: return occupancy_of<5>(threads, smem, occ);
+        case 6: return occupancy_of<6>(threads, smem, occ);
+        default: return CVAR_ERR_COPULA;
+    }
+}
+
+// The dynamic shared-memory limit is an attribute of a kernel instantiation on a device, not of a plan: every
+// instantiation of the variant is opted in to the device maximum, so that plans of different grids can coexist.
+template <int KV>
+int opt_in_smem(size_t bytes) {
+    int rc = set_smem(solve_kernel<KV, false>, bytes);
+    if (!rc) rc = set_smem(solve_kernel<KV, true>, bytes);
+    if (!rc) rc = set_smem(strip_mass_kernel<KV>, bytes);
+    return rc;
+}
+int opt_in_smem_variant(int kv, size_t bytes) {
+    switch (kv) {
+        case 0: return opt_in_smem<0>(bytes);
+        case 1: return opt_in_smem<1>(bytes);
+        case 2: return opt_in_smem<2>(bytes);
+        case 3: return opt_in_smem<3>(bytes);
+        case 4: return opt_in_smem<4>(bytes);
+        case 5: return opt_in_smem<5>(bytes);
+        case 6: return opt_in_smem<6>(bytes);
+        default: return CVAR_ERR_COPULA;
+    }
+}
+
+// CTA size (measured on B200, tools/sweep_cta_threads.sh): registers cap an SM at 16 resident warps whatever the CTA
+// size, and the more independent CTAs share those warps the better their barrier phases interleave.  So: the smallest
+// of 64 / 128 / 256 / 512 threads whose resident CTAs (shared memory, registers) still add up to the most warps.
+int best_cta_threads(int kv, size_t smem, int* threads_out, int* resident_out) {
+    int best_threads = 0, best_resident = -1;
+    for (int th = 64; th <= CTA_THREADS_LARGE; th *= 2) {
+        int occ = 0;
+        int rc = solve_occupancy(kv, th, smem, &occ);
+        if (rc) return rc;
+        const int resident = std::min(occ * th, 512);
+        if (resident > best_resident) { best_resident = resident; best_threads = th; }
+    }
+    *threads_out = best_threads;
+    *resident_out = best_resident;
+    return 0;
 }
 
 // Days in ascending order of the portfolio-variance proxy (most expensive solves first); nullptr when the
@@ -392,8 +450,28 @@ int cvar_plan_create(const cvar_desc_t* desc, const double* x, const double* dx,
             }
         }
     }
-    p->smem_bytes = smem_bytes_for(n, p->kernel_variant);
+    p->smem_bytes = smem_bytes_for(n, p->kernel_variant, 0);
     if (p->smem_bytes > (size_t)prop.sharedMemPerBlockOptin) { delete p; return CVAR_ERR_SMEM; }
+    rc = opt_in_smem_variant(p->kernel_variant, prop.sharedMemPerBlockOptin);
+    if (rc) { delete p; return rc; }
+    // One-lookup power table (cvar_math.cuh): as many octaves of t as fit without costing the SM a resident warp.
+    int pow_octaves = 0;
+    if (kv_pow_degree(p->kernel_variant) > 0 && POW_FAST_MODE > 0) {
+        int want = POW_FAST_MAX_OCTAVES;
+        if (const char* env = std::getenv("CVAR_POW_OCTAVES")) want = std::max(0, std::min(POW_FAST_MAX_OCTAVES, std::atoi(env)));
+        int th0 = 0, res0 = 0;
+        rc = best_cta_threads(p->kernel_variant, p->smem_bytes, &th0, &res0);
+        if (rc) { delete p; return rc; }
+        for (int oct = want; oct >= 1; --oct) {
+            const size_t bytes = smem_bytes_for(n, p->kernel_variant, oct);
+            if (bytes > (size_t)prop.sharedMemPerBlockOptin) continue;
+            int th = 0, res = 0;
+            rc = best_cta_threads(p->kernel_variant, bytes, &th, &res);
+            if (rc) { delete p; return rc; }
+            if ((res >= res0 && th <= th0) || std::getenv("CVAR_POW_OCTAVES")) { pow_octaves = oct; break; }
+        }
+        p->smem_bytes = smem_bytes_for(n, p->kernel_variant, pow_octaves);
+    }
 
     // ---- run constants -------------------------------------------------------------------
     KernelParams& kp = p->kp;
@@ -548,6 +626,15 @@ int cvar_plan_create(const cvar_desc_t* desc, const double* x, const double* dx,
         powtab_build_kernel<<<1, POW_MTAB, 0, p->stream>>>(0.5 * (desc->nu + 2.0), p->d_powtab);
         PLAN_TRY(cudaGetLastError());
         kp.powtab = p->d_powtab;
+        if (pow_octaves > 0) {
+            const int entries = pow_octaves * POW_MTAB;
+            PLAN_TRY(cudaMalloc(&p->d_powfast, sizeof(double) * entries * POW_FAST_ENTRY_DOUBLES));
+            powfast_build_kernel<<<(entries + 255) / 256, 256, 0, p->stream>>>(0.5 * (desc->nu + 2.0), pow_octaves, p->d_powfast);
+            PLAN_TRY(cudaGetLastError());
+            kp.powfast = p->d_powfast;
+            kp.pow_octaves = pow_octaves;
+            kp.pow_fast_limit = std::ldexp(1.0, pow_octaves) * (1.0 - 1e-6);   // margin: the row check looks at the range ends only
+        }
     }
     PLAN_TRY(cudaStreamSynchronize(p->stream));
 
@@ -570,27 +657,11 @@ int cvar_plan_create(const cvar_desc_t* desc, const double* x, const double* dx,
         const int v = std::atoi(env);
         if (v == 1 || v == 2 || v == 4) p->cluster_forced = v;
     }
-#define CVAR_PREP(KV)                                                                                              \
-    case KV:                                                                                                       \
-        PLAN_TRY((cudaError_t)set_smem(solve_kernel<KV, false>, p->smem_bytes));                                   \
-        PLAN_TRY((cudaError_t)set_smem(solve_kernel<KV, true>, p->smem_bytes));                                    \
-        PLAN_TRY((cudaError_t)set_smem(strip_mass_kernel<KV>, p->smem_bytes));                                     \
-        if (p->cta_threads == 0) {                                                                                 \
-            int best_threads = 0, best_resident = -1;                                                              \
-            for (int th = 64; th <= CTA_THREADS_LARGE; th *= 2) {                                                  \
-                PLAN_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, solve_kernel<KV, false>, th, p->smem_bytes)); \
-                const int resident = std::min(occ * th, 512);                                                      \
-                if (resident > best_resident) { best_resident = resident; best_threads = th; }                     \
-            }                                                                                                      \
-            p->cta_threads = best_threads;                                                                         \
-        }                                                                                                          \
-        PLAN_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, solve_kernel<KV, false>, p->cta_threads, p->smem_bytes)); \
-        break;
-    switch (p->kernel_variant) {
-        CVAR_PREP(0) CVAR_PREP(1) CVAR_PREP(2) CVAR_PREP(3) CVAR_PREP(4) CVAR_PREP(5) CVAR_PREP(6)
-        default: break;
+    if (p->cta_threads == 0) {
+        int resident = 0;
+        PLAN_TRY((cudaError_t)best_cta_threads(p->kernel_variant, p->smem_bytes, &p->cta_threads, &resident));
     }
-#undef CVAR_PREP
+    PLAN_TRY((cudaError_t)solve_occupancy(p->kernel_variant, p->cta_threads, p->smem_bytes, &occ));
     p->ctas_per_sm = occ;
     // how many 2- and 4-CTA clusters of the large CTA fit the device at once (GPC boundaries make this less than
     // #SMs / size); a failure here only disables the cluster split
@@ -634,6 +705,7 @@ int cvar_plan_destroy(cvar_plan_t* p) {
     cudaFree(p->d_logtab);
     cudaFree(p->d_exptab);
     cudaFree(p->d_powtab);
+    cudaFree(p->d_powfast);
     cudaFree(p->d_state_cdf);
     cudaFree(p->d_state_pdf);
     cudaFree(p->d_ws);

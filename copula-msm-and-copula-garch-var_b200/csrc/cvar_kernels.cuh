@@ -88,6 +88,9 @@ struct KernelParams {
     const double* exptab;  // gaussian / student: 2^(i/EXPTAB_SIZE), EXPTAB_SIZE entries (global; staged to shared memory)
     double powc[POW_MAX_DEG + 1];  // student pow variants: polynomial for (1+f)^(-(nu+2)/2), |f| <= POW_FMAX
     const double* powtab;  // student pow variants: r_i^c (POW_MTAB) then 2^(-c e) (POW_ETAB)
+    const double* powfast; // student pow variants: one-lookup table over the first pow_octaves octaves of t (cvar_math.cuh)
+    int pow_octaves;       // 0: no one-lookup table
+    double pow_fast_limit; // rows whose quadratic form stays below this use the one-lookup table
     const double* x;
     const double* dx;
     const double* sigma_states;  // [2][q] or nullptr
@@ -118,23 +121,25 @@ struct Smem {
     double* memo;   // [MEMO_SIZE][4]: (lo, hi, mass, cells) of strips already integrated for an earlier alpha
     double* ptab;   // [POW_MTAB + POW_ETAB] student pow variants (aliases the ltab/etab region)
     unsigned ptab_s;  // shared-window address of ptab
+    double* pfast;    // one-lookup power table (pow_octaves * POW_MTAB entries), 16-byte aligned
+    unsigned pfast_s; // its shared-window address minus the index bias (see pow_neg_c_fast)
 };
 
 // doubles of per-variant lookup tables staged in shared memory (after the fixed part)
-__host__ __device__ constexpr int table_doubles(int kv) {
+__host__ __device__ constexpr int table_doubles(int kv, int pow_octaves) {
     return kv == KV_GAUSSIAN ? EXPTAB_SIZE
          : kv == KV_STUDENT  ? LOGTAB_SIZE + EXPTAB_SIZE
          : kv == KV_PLACKETT ? 0
-                             : POW_MTAB + POW_ETAB;
+                             : POW_MTAB + POW_ETAB + pow_octaves * POW_MTAB * POW_FAST_ENTRY_DOUBLES;
 }
 
-__host__ __device__ inline size_t smem_bytes_for(int n, int kv) {
+__host__ __device__ inline size_t smem_bytes_for(int n, int kv, int pow_octaves) {
     size_t npad = (size_t)((n + 3) & ~3);
-    return npad * 8 * 5 + npad * 2 * 3 + 2 * MAX_CTA_WARPS * 8 + 2 * MAX_CTA_WARPS * 4 + 16 + 64 + MEMO_SIZE * 4 * 8 +
-           (size_t)table_doubles(kv) * 8;
+    return npad * 8 * 5 + npad * 2 * 3 + 2 * MAX_CTA_WARPS * 8 + 2 * MAX_CTA_WARPS * 4 + 16 + 64 + MEMO_SIZE * 4 * 8 + 8 +
+           (size_t)table_doubles(kv, pow_octaves) * 8;
 }
 
-__device__ __forceinline__ Smem carve(unsigned char* base, int n, int kv) {
+__device__ __forceinline__ Smem carve(unsigned char* base, int n, int kv, int pow_octaves) {
     size_t npad = (size_t)((n + 3) & ~3);
     Smem S;
     double* d = reinterpret_cast<double*>(base);
@@ -153,18 +158,23 @@ __device__ __forceinline__ Smem carve(unsigned char* base, int n, int kv) {
     S.cl_cells = reinterpret_cast<unsigned*>(S.live + 8);
     S.memo = reinterpret_cast<double*>(S.live + 4 + 12);  // 64 bytes after `live`: stays 8-byte aligned
     double* tables = S.memo + MEMO_SIZE * 4;              // variant-specific tables, see table_doubles()
+    tables += (reinterpret_cast<size_t>(tables) >> 3) & 1;   // 16-byte aligned (the u16 arrays leave it 8-byte aligned)
     S.ltab = tables;                                      // KV_STUDENT: ltab then etab
     S.etab = kv == KV_STUDENT ? tables + LOGTAB_SIZE : tables;
     S.ptab = tables;
     S.ptab_s = (unsigned)__cvta_generic_to_shared(tables);
+    S.pfast = tables + POW_MTAB + POW_ETAB;
+    S.pfast_s = S.ptab_s + (unsigned)((POW_MTAB + POW_ETAB) * 8) - (unsigned)((1023 << POW_BITS) * 8 * POW_FAST_ENTRY_DOUBLES);
+    (void)pow_octaves;
     return S;
 }
 
 // ---------------------------------------------------------------------------------------------
 // stage 0: per-axis quantities
 // ---------------------------------------------------------------------------------------------
+// Returns true when every cell of the day has a quadratic form below pow_fast_limit (Student-t power variants).
 template <int COPULA>
-__device__ void stage0(const KernelParams& P, const double* __restrict__ dayp, const Smem& S) {
+__device__ bool stage0(const KernelParams& P, const double* __restrict__ dayp, const Smem& S) {
     const int n = P.n, q = P.q;
     if (threadIdx.x < 4) S.live[threadIdx.x] = 0;
     if (COPULA == KV_STUDENT)
@@ -173,6 +183,8 @@ __device__ void stage0(const KernelParams& P, const double* __restrict__ dayp, c
         for (int k = threadIdx.x; k < EXPTAB_SIZE; k += blockDim.x) S.etab[k] = P.exptab[k];
     if (kv_pow_degree(COPULA) > 0)
         for (int k = threadIdx.x; k < POW_MTAB + POW_ETAB; k += blockDim.x) S.ptab[k] = P.powtab[k];
+    if (kv_pow_degree(COPULA) > 0 && POW_FAST_MODE > 0)
+        for (int k = threadIdx.x; k < P.pow_octaves * POW_MTAB * POW_FAST_ENTRY_DOUBLES; k += blockDim.x) S.pfast[k] = P.powfast[k];
     __syncthreads();
     const bool swap = (P.compat & 1u) != 0;
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
@@ -251,6 +263,23 @@ __device__ void stage0(const KernelParams& P, const double* __restrict__ dayp, c
         }
     }
     __syncthreads();
+    if (kv_pow_degree(COPULA) > 0 && POW_FAST_MODE > 0) {
+        if (P.pow_octaves == 0) return false;
+        // the quadratic form is convex along a row, so its maximum over the live columns sits at one of their ends
+        const int j_lo = S.live[2], j_hi = n - S.live[3];
+        int slow = 0;
+        if (j_hi > j_lo) {
+            const double a_lo = S.in[j_lo].x, a_hi = S.in[j_hi - 1].x;
+            for (int i = threadIdx.x; i < n; i += blockDim.x) {
+                const double y0 = S.out0[i];
+                const double m0 = P.g_out_scale * y0, c0 = fma(y0 * y0, P.inv_nu, 1.0);
+                const double d = fmax(fabs(a_lo - m0), fabs(a_hi - m0));
+                slow |= !(fma(d, d, c0) < P.pow_fast_limit);
+            }
+        }
+        return __syncthreads_or(slow) == 0;
+    }
+    return false;
 }
 
 // per-plan tables of the mixture marginals: one thread per (asset, state, axis point)
@@ -286,6 +315,25 @@ __device__ __forceinline__ int count_le(const double* __restrict__ xs, double g,
             hi = mid;
     }
     return lo;
+}
+
+// The same count when BOTH bracket ends are counts at bracketing levels (lo < hi, the bisection passes): the level
+// sought is the midpoint of the two, so on a (locally) uniform axis the count is the midpoint of the bracket give or
+// take one.  Two comparisons settle it in the common case; rows whose bracket straddles a change of spacing fall back
+// to the bisection on what is left.  Exact like count_le: every decision is a comparison with an axis value.
+__device__ __forceinline__ int count_between(const double* __restrict__ xs, double g, int lo, int hi) {
+    int k = (lo + hi + 1) >> 1;   // lo < k <= hi
+    const double below = xs[k - 1], above = xs[k < hi ? k : k - 1];   // two independent loads
+    if (below <= g) {
+        if (k < hi && above <= g) {
+            ++k;
+            if (k < hi && xs[k] <= g) k = count_le(xs, g, k + 1, hi);
+        }
+    } else {
+        --k;
+        if (k > lo && !(xs[k - 1] <= g)) k = count_le(xs, g, lo, k - 1);
+    }
+    return k;
 }
 
 // Row ownership.  Rows are dealt to warps in blocks of 32 (lane = row within the block, so adjacent lanes walk
@@ -341,13 +389,31 @@ __device__ __forceinline__ int count_row(const KernelParams& P, const Smem& S, d
     return max(k, P.cmin);
 }
 
+// Rows whose bracket [lo, hi] has closed (no grid point left between the two boundaries) can never move again during
+// the bisection of the current alpha.  Every thread keeps one bit per owned row: closed rows are not even looked at
+// any more (their boundary entries go stale and are never read), and a round none of whose 32 rows is open costs
+// one warp vote.  By the tenth step nine rows in ten are closed.
+//   open: bit m set = the row of round m may still move;  at_lo / at_hi: the boundary found in the current pass
+//   equals the lower / upper end of the row's bracket, so the row closes if the bracket continues with that end.
+struct RowMask {
+    unsigned open, at_lo, at_hi;
+};
+
 // ctarget[i] = count_row(q) for every outer row this thread owns
 __device__ __forceinline__ void count_rows(const KernelParams& P, const Smem& S, const Part& pt, double q, u16* ctarget,
-                                           const u16* slo, const u16* shi) {
+                                           const u16* slo, const u16* shi, RowMask* rm = nullptr) {
     const int n = P.n;
     for (int m = 0; m < owned_rounds(pt, n); ++m) {
         const int i = owned_row(pt, m);
-        if (i < n) ctarget[i] = (u16)count_row(P, S, q, i, slo ? (int)slo[i] : 0, shi ? (int)shi[i] : n);
+        if (i < n && (!rm || ((rm->open >> m) & 1u))) {
+            const int lo = slo ? (int)slo[i] : 0, hi = shi ? (int)shi[i] : n;
+            const int k = count_row(P, S, q, i, lo, hi);
+            ctarget[i] = (u16)k;
+            if (rm) {
+                if (k == lo) rm->at_lo |= 1u << m;
+                if (k == hi) rm->at_hi |= 1u << m;
+            }
+        }
     }
 }
 
@@ -368,10 +434,12 @@ struct Row<0> {  // Gaussian:  W = rowfac * 2^( l1[j] - (y1'[j] - m0)^2 )
         const double d = a - m0;
         return exp2_tab(fma(-d, d, b), S.etab);
     }
+    template <bool FAST>
     __device__ __forceinline__ double add_cell(const KernelParams&, const Smem& S, double a, double b, double acc) const {
         const double d = a - m0;
         return exp2_tab_add(fma(-d, d, b), S.etab, acc);
     }
+    __device__ __forceinline__ double quad_form(double) const { return 0.0; }
 };
 
 template <>
@@ -388,11 +456,13 @@ struct Row<1> {  // Student-t: W = rowfac * 2^( l1[j] - (nu+2)/2 * log2( c0 + (y
         const double t = fma(d, d, c0);  // >= 1
         return exp2_tab(scaled_log2_plus(t, b, P.negc, P.qc, S.ltab), S.etab);
     }
+    template <bool FAST>
     __device__ __forceinline__ double add_cell(const KernelParams& P, const Smem& S, double a, double b, double acc) const {
         const double d = a - m0;
         const double t = fma(d, d, c0);
         return exp2_tab_add(scaled_log2_plus(t, b, P.negc, P.qc, S.ltab), S.etab, acc);
     }
+    __device__ __forceinline__ double quad_form(double) const { return 0.0; }
 };
 
 template <int DEG>
@@ -409,8 +479,17 @@ struct RowStudentPow {  // Student-t: W = rowfac * A1[j] * ( c0 + (y1'[j] - m0)^
         const double t = fma(d, d, c0);  // >= 1
         return pow_neg_c<DEG>(t, b, P.powc, S.ptab_s, P.seed_mask, P.seed_half);
     }
+    template <bool FAST>
     __device__ __forceinline__ double add_cell(const KernelParams& P, const Smem& S, double a, double b, double acc) const {
+        if (FAST) {
+            const double d = a - m0;
+            return acc + pow_neg_c_fast<DEG>(fma(d, d, c0), b, P.powc, S.pfast_s, P.seed_mask, P.seed_half);
+        }
         return acc + cell(P, S, a, b);   // contracts to one FMA with the last product of pow_neg_c
+    }
+    __device__ __forceinline__ double quad_form(double a) const {
+        const double d = a - m0;
+        return fma(d, d, c0);
     }
 };
 template <> struct Row<KV_STUDENT_POW5> : RowStudentPow<5> {};
@@ -439,9 +518,11 @@ struct Row<2> {  // Plackett (the reference's formula, plackett.py:66-69), u = r
         const double dd = fma(v, fma(v, qa, qb), qc);
         return (a1 * num) * rcp_cell(dd * dd);
     }
+    template <bool FAST>
     __device__ __forceinline__ double add_cell(const KernelParams& P, const Smem& S, double v, double a1, double acc) const {
         return acc + cell(P, S, v, a1);
     }
+    __device__ __forceinline__ double quad_form(double) const { return 0.0; }
 };
 
 struct StripResult {
@@ -452,6 +533,8 @@ struct StripResult {
 
 struct Live {  // live window of rows / columns (cells outside have an infinite copula quantile)
     int i_lo, i_hi, j_lo, j_hi;
+    bool full;      // the window is the whole grid (always, on mixture marginals whose tails do not saturate)
+    bool day_fast;  // Student-t power variants: every cell of the day is in the range of the one-lookup table
 };
 
 // block-wide (cluster-wide when the day is split over a cluster) deterministic sum; every thread of every CTA
@@ -504,69 +587,187 @@ __device__ __forceinline__ StripResult block_reduce(const Smem& S, const Part& p
 // One strip of the bisection.
 //
 // Every thread owns a fixed set of outer rows (owned_row) for the whole solve: it finds the row's new boundary
-// index by an exact binary search (when q_new is given), then walks the row's cells [a, b) itself with
-// CELLS_IN_FLIGHT independent cells per trip.  Adjacent lanes own adjacent rows, whose ranges are shifted
-// by about one column, so the 16-byte shared-memory loads of a warp fall on consecutive addresses.
+// index by an exact search (when q_new is given); the row's cells [a, b) are then summed in one of two ways.
+//
+//  * Column sweep (the 32 rows of a warp's block all hold cells and overlap in at least BCAST_MIN_BODY columns).
+//    The lanes of a GROUP of CVAR_BCAST_GROUP adjacent rows read the SAME column in the same trip -- one 16-byte
+//    shared-memory word per group, a broadcast -- and the groups are skewed against each other by the shift of
+//    their rows' ranges, so that all of them start and end together.  A warp-wide column load then costs ONE
+//    shared-memory wavefront (the groups' words are steered into distinct banks) instead of the four of 32
+//    distinct words, and the lanes of a group meet the lookup tables of the cell at neighbouring entries.  The
+//    shared-memory data pipe was the binding unit of the lane-per-row walk (ncu: 7.6 wavefronts per warp-cell,
+//    pipe saturated inside the loop); the sweep needs about three.
+//  * Lane-per-row walk for what is left: the columns of a row outside the common window (a ramp of at most
+//    ~GROUP columns per end), blocks at the edge of the strip and the thin strips of the late iterations.
+//
 // There is no per-strip barrier besides the one inside the block reduction, and the boundary arrays are
 // only ever touched by their owning thread.
 //   bound arrays: ca == nullptr means the constant lower end cmin; cnew (may alias ca or cb) receives
 //   count(q_new) searched inside [slo[i], shi[i]] before the row is summed.
+#ifndef CVAR_BCAST_GROUP
+#define CVAR_BCAST_GROUP 0   // 0: lane-per-row walk only; 2 / 4 / 8 / 16: skewed groups; 32: the whole warp on one column
+#endif
+#ifndef CVAR_BCAST_MIN_ROW
+#define CVAR_BCAST_MIN_ROW 16   // shortest row of the block below which the sweep is not even attempted
+#endif
+#ifndef CVAR_PREFETCH
+#define CVAR_PREFETCH 1      // sweep: the next trip's columns are loaded before this trip's cells are evaluated
+#endif
+constexpr int BCAST_GROUP = CVAR_BCAST_GROUP;
+constexpr int BCAST_MIN_BODY = 8;
+
+// Sum of the cells [s, e) of this lane's row.  All 32 lanes of the warp must call it (warp votes / shuffles
+// inside); lanes without cells pass s == e.
+template <int COPULA, bool FAST>
+__device__ __forceinline__ double walk_block(const KernelParams& P, const Smem& S, const Row<COPULA>& row, int s, int e) {
+    constexpr int CIF = CellsInFlight<COPULA>::value;
+    constexpr unsigned FULL = 0xffffffffu;
+    constexpr int G = BCAST_GROUP > 0 ? BCAST_GROUP : 32;
+#ifdef CVAR_EXPERIMENT_NO_CELLS   // timing experiment: everything but the cell loops (results are meaningless)
+    return 1e-9 * (double)(e - s);
+#endif
+    double acc[CIF];
+#pragma unroll
+    for (int c = 0; c < CIF; ++c) acc[c] = 0.0;
+    int left_end = s, right_begin = s;   // lane-per-row segments [s, left_end) and [right_begin, e)
+    if (BCAST_GROUP > 0 && __all_sync(FULL, e - s >= CVAR_BCAST_MIN_ROW)) {
+        int off = 0;   // this lane reads column (trip - off)
+        if (G < 32) {
+            constexpr int NG = 32 / G;
+            const int lane = threadIdx.x & 31, g = lane / G;
+            // align the groups' first columns; then make the offsets distinct modulo the number of groups, which puts
+            // the groups' 16-byte words into different banks
+            off = __shfl_sync(FULL, s, 0) - __shfl_sync(FULL, s, lane & ~(G - 1));
+            if (NG <= 8)
+                off += (g - off) & (NG - 1);
+            else   // 16 pairs: their words must fall on every 16-byte bank group exactly twice (offsets 2g + g/4 modulo 8)
+                off += ((2 * g + (g >> 2)) - off) & 7;
+        }
+        const int t0 = __reduce_max_sync(FULL, s + off);
+        const int t1 = __reduce_min_sync(FULL, e + off);
+        if (t1 - t0 >= BCAST_MIN_BODY) {
+            const int trips = (t1 - t0) / CIF;
+            const double2* col = S.in + (t0 - off);
+            if (CVAR_PREFETCH) {
+                double2 v[CIF];
+#pragma unroll
+                for (int c = 0; c < CIF; ++c) v[c] = col[c];
+                for (int k = 0; k < trips; ++k) {
+                    col += CIF;
+                    double2 w[CIF];   // the last trip reads CIF columns past the window: still inside the shared arrays, unused
+#pragma unroll
+                    for (int c = 0; c < CIF; ++c) w[c] = col[c];
+#pragma unroll
+                    for (int c = 0; c < CIF; ++c) acc[c] = row.template add_cell<FAST>(P, S, v[c].x, v[c].y, acc[c]);
+#pragma unroll
+                    for (int c = 0; c < CIF; ++c) v[c] = w[c];
+                }
+            } else {
+                for (int k = 0; k < trips; ++k, col += CIF) {
+                    double2 v[CIF];
+#pragma unroll
+                    for (int c = 0; c < CIF; ++c) v[c] = col[c];
+#pragma unroll
+                    for (int c = 0; c < CIF; ++c) acc[c] = row.template add_cell<FAST>(P, S, v[c].x, v[c].y, acc[c]);
+                }
+            }
+            left_end = t0 - off;
+            right_begin = t0 - off + trips * CIF;
+        }
+    }
+#pragma unroll 1
+    for (int seg = (BCAST_GROUP > 0 ? 0 : 1); seg < 2; ++seg) {
+        int j = seg ? right_begin : s;
+        const int je = seg ? e : left_end;
+        for (; j + CIF <= je; j += CIF) {
+            double2 v[CIF];
+#pragma unroll
+            for (int c = 0; c < CIF; ++c) v[c] = S.in[j + c];
+#pragma unroll
+            for (int c = 0; c < CIF; ++c) acc[c] = row.template add_cell<FAST>(P, S, v[c].x, v[c].y, acc[c]);
+        }
+        for (; j < je; ++j) {
+            const double2 v = S.in[j];
+            acc[0] = row.template add_cell<FAST>(P, S, v.x, v.y, acc[0]);
+        }
+    }
+    double rowsum = acc[0];
+#pragma unroll
+    for (int c = 1; c < CIF; ++c) rowsum += acc[c];
+    return rowsum;
+}
+
+// cnew[i] = count(q_new) for every owned row, searched inside [slo[i], shi[i]] (nullptr: open end), then the cells
+// [ca[i], cb[i]) of the row are summed; ca == nullptr is the constant lower end cmin, and ca / cb may alias cnew, slo or
+// shi -- the values then come from registers instead of a shared-memory round trip.
 template <int COPULA>
-__device__ StripResult strip_pass(const KernelParams& P, const Smem& S, const Part& pt, const Live& L, int& parity, bool do_count,
+__device__ StripResult strip_pass(const KernelParams& P, const Smem& S, const Part& pt, const Live& L, int& parity,
                                   double q_new, u16* cnew, const u16* slo, const u16* shi, const u16* ca,
-                                  const u16* cb, bool poison_mode) {
-    constexpr int CELLS_IN_FLIGHT = CellsInFlight<COPULA>::value;
+                                  const u16* cb, bool poison_mode, RowMask* rm = nullptr) {
+    constexpr unsigned FULL = 0xffffffffu;
     const int n = P.n;
     double total = 0.0;
     unsigned cells = 0;
     bool poison = false;
+    const bool between = slo && shi && P.w0 > 0.0;   // both bracket ends known and ordered: midpoint search
     for (int m = 0; m < owned_rounds(pt, n); ++m) {
         const int i = owned_row(pt, m);
-        if (i >= n) continue;
-        if (do_count) {
+        const bool open = i < n && (!rm || ((rm->open >> m) & 1u));
+        if (rm && !__any_sync(FULL, open)) continue;   // the 32 rows of this block are closed
+        int s = 0, e = 0;
+        if (open) {
+            const double xi = S.xs[i];
             const int lo = slo ? (int)slo[i] : 0, hi = shi ? (int)shi[i] : n;
-            if (slo && shi && lo == hi) {   // no grid point of this row between the bracket ends: nothing can move
-                cnew[i] = (u16)lo;
-                continue;
+            int k = lo;
+            if (!(slo && shi && lo == hi)) {   // else: no grid point of this row between the bracket ends, nothing can move
+                if (between)
+                    k = max(count_between(S.xs, inner_bound(q_new, xi, P.w0, P.w1, P.rw0_exact), lo, hi), P.cmin);
+                else
+                    k = count_row(P, S, q_new, i, lo, hi);
+                s = !ca ? P.cmin : ca == cnew ? k : ca == slo ? lo : ca == shi ? hi : (int)ca[i];
+                e = cb == cnew ? k : cb == slo ? lo : cb == shi ? hi : (int)cb[i];
             }
-            cnew[i] = (u16)count_row(P, S, q_new, i, lo, hi);
-        }
-        int s = ca ? (int)ca[i] : P.cmin;
-        int e = (int)cb[i];
+            cnew[i] = (u16)k;
+            if (rm) {
+                if (k == lo) rm->at_lo |= 1u << m;
+                if (k == hi) rm->at_hi |= 1u << m;
+            }
 #ifdef CVAR_DEBUG_ASSERT
-        if (s < 0 || e > n || (do_count && (int)cnew[i] > n)) __trap();
+            if (s < 0 || e > n || k > n) __trap();
 #endif
-        if (e <= s) continue;
-        cells += (unsigned)(e - s);
-        if (i < L.i_lo || i >= L.i_hi) {
-            poison = true;
-            continue;
+            if (e > s) {
+                cells += (unsigned)(e - s);
+                if (!L.full) {
+                    if (i < L.i_lo || i >= L.i_hi) {
+                        poison = true;
+                        e = s;
+                    } else {
+                        if (s < L.j_lo || e > L.j_hi) poison = true;
+                        s = max(s, L.j_lo);
+                        e = min(e, L.j_hi);
+                    }
+                }
+            }
         }
-        if (s < L.j_lo || e > L.j_hi) poison = true;
-        s = max(s, L.j_lo);
-        e = min(e, L.j_hi);
-        if (e <= s) continue;
+        const bool act = e > s;
+        if (!__any_sync(FULL, act)) continue;
+        if (!act) s = e = 0;
         Row<COPULA> row;
-        row.load(P, S, i);
-        double acc[CELLS_IN_FLIGHT];
-#pragma unroll
-        for (int c = 0; c < CELLS_IN_FLIGHT; ++c) acc[c] = 0.0;
-        int j = s;
-        for (; j + CELLS_IN_FLIGHT <= e; j += CELLS_IN_FLIGHT) {
-            double2 v[CELLS_IN_FLIGHT];
-#pragma unroll
-            for (int c = 0; c < CELLS_IN_FLIGHT; ++c) v[c] = S.in[j + c];
-#pragma unroll
-            for (int c = 0; c < CELLS_IN_FLIGHT; ++c) acc[c] = row.add_cell(P, S, v[c].x, v[c].y, acc[c]);
+        row.load(P, S, act ? i : 0);
+        double rowsum;
+        bool fast = false;
+        if (kv_pow_degree(COPULA) > 0 && POW_FAST_MODE > 0 && P.pow_octaves > 0) {
+            fast = L.day_fast;
+            if (!fast) {   // the quadratic form is convex along the row: check the two ends of this strip's range
+                const double tmax = act ? fmax(row.quad_form(S.in[s].x), row.quad_form(S.in[e - 1].x)) : 0.0;
+                fast = !__any_sync(FULL, !(tmax < P.pow_fast_limit));
+            }
         }
-        for (; j < e; ++j) {
-            const double2 v = S.in[j];
-            acc[0] = row.add_cell(P, S, v.x, v.y, acc[0]);
-        }
-        double rowsum = acc[0];
-#pragma unroll
-        for (int c = 1; c < CELLS_IN_FLIGHT; ++c) rowsum += acc[c];
-        total = fma(row.fac, rowsum, total);
+        if (kv_pow_degree(COPULA) > 0 && POW_FAST_MODE > 0 && fast)
+            rowsum = walk_block<COPULA, true>(P, S, row, s, e);
+        else
+            rowsum = walk_block<COPULA, false>(P, S, row, s, e);
+        if (act) total = fma(row.fac, rowsum, total);
     }
     StripResult r = block_reduce(S, pt, parity, total, cells, poison && poison_mode);
     if (r.poisoned) r.mass = NAN;
@@ -581,12 +782,12 @@ __device__ __forceinline__ StripResult strip_memo(const KernelParams& P, const S
                                                   bool use_memo, bool remember, int memo_visible, int& memo_n,
                                                   double a, double b,
                                                   double q_new, u16* cnew, const u16* slo, const u16* shi,
-                                                  const u16* ca, const u16* cb, bool poison_mode) {
+                                                  const u16* ca, const u16* cb, bool poison_mode, RowMask* rm = nullptr) {
     if (use_memo) {
         for (int k = 0; k < memo_visible; ++k) {
             const double* e = S.memo + 4 * k;
             if (e[0] == a && e[1] == b) {
-                count_rows(P, S, pt, q_new, cnew, slo, shi);  // the boundary indices are still needed downstream
+                count_rows(P, S, pt, q_new, cnew, slo, shi, rm);  // the boundary indices are still needed downstream
                 StripResult r;
                 r.mass = e[2];
                 r.cells = (unsigned)e[3];
@@ -595,7 +796,7 @@ __device__ __forceinline__ StripResult strip_memo(const KernelParams& P, const S
             }
         }
     }
-    const StripResult r = strip_pass<COPULA>(P, S, pt, L, parity, true, q_new, cnew, slo, shi, ca, cb, poison_mode);
+    const StripResult r = strip_pass<COPULA>(P, S, pt, L, parity, q_new, cnew, slo, shi, ca, cb, poison_mode, rm);
     if (use_memo && remember && memo_n < MEMO_SIZE) {
         if (threadIdx.x == 0) {
             double* e = S.memo + 4 * memo_n;
@@ -617,7 +818,7 @@ solve_kernel(KernelParams P, const double* __restrict__ day_params, long long T,
              const int* __restrict__ order, unsigned* __restrict__ traj, double* __restrict__ mass_out,
              unsigned long long* __restrict__ cells_out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const Smem S = carve(smem_raw, P.n, COPULA);
+    const Smem S = carve(smem_raw, P.n, COPULA, P.pow_octaves);
     Part pt = make_part(0, 1, P.n);
     if (CLUSTER) {
         cooperative_groups::cluster_group cluster = cooperative_groups::this_cluster();
@@ -627,15 +828,24 @@ solve_kernel(KernelParams P, const double* __restrict__ day_params, long long T,
     const long long unit = blockIdx.x / pt.size;
     const long long day = order ? order[unit] : unit;
     const int stride = (P.marginal == 0) ? 2 : 2 * P.q;
-    stage0<COPULA>(P, day_params + day * stride, S);
+#ifdef CVAR_PROFILE_PHASES   // experiment: thread 0's clock per phase goes out through traj / mass / cells (results are overwritten)
+    const long long prof_t0 = clock64();
+    long long prof_thin = 0, prof_probe = 0;
+#endif
+    const bool day_fast = stage0<COPULA>(P, day_params + day * stride, S);
+#ifdef CVAR_PROFILE_PHASES
+    const long long prof_t1 = clock64();
+#endif
 
     Live L;
+    L.day_fast = day_fast;
     if (COPULA == 2) {
         L.i_lo = 0; L.i_hi = P.n; L.j_lo = 0; L.j_hi = P.n;
     } else {
         L.i_lo = S.live[0]; L.i_hi = P.n - S.live[1];
         L.j_lo = S.live[2]; L.j_hi = P.n - S.live[3];
     }
+    L.full = L.i_lo == 0 && L.i_hi == P.n && L.j_lo == 0 && L.j_hi == P.n;
     // Q5: NaN cells are zeroed on the single-normal path, poison the strip on the mixture path
     const bool poison_mode = (COPULA != 2) && (P.marginal == 1) && ((P.compat & 4u) != 0);
     int parity = 0;
@@ -652,7 +862,7 @@ solve_kernel(KernelParams P, const double* __restrict__ day_params, long long T,
         const int memo_visible = memo_n;
         // --- probe 1: F(first)  (calc_var_class.py:114-119)
         if (!have_f3) {
-            f3 = strip_pass<COPULA>(P, S, pt, L, parity, true, P.first, S.c[0], nullptr, nullptr, nullptr, S.c[0], poison_mode);
+            f3 = strip_pass<COPULA>(P, S, pt, L, parity, P.first, S.c[0], nullptr, nullptr, nullptr, S.c[0], poison_mode);
             have_f3 = true;
         } else {
             count_rows(P, S, pt, P.first, S.c[0], nullptr, nullptr);
@@ -691,19 +901,32 @@ solve_kernel(KernelParams P, const double* __restrict__ day_params, long long T,
         }
         bool stack = !(hi == P.second_lo || hi == P.second_hi);  // :160
         unsigned dec = 0, zer = 0;
+        RowMask rows = {0xffffffffu, 0u, 0u};
+        RowMask* rm = owned_rounds(pt, P.n) <= 32 ? &rows : nullptr;
         if (kase != 4) {
+#ifdef CVAR_PROFILE_PHASES
+            prof_probe = clock64() - prof_t1;
+#endif
             for (int k = 0; k < P.max_iter; ++k) {
+#ifdef CVAR_PROFILE_PHASES
+                const long long prof_k0 = clock64();
+#endif
                 const double mid = (lo + hi) / 2;
                 const double a = stack ? lo : mid, b = stack ? mid : hi;
                 const StripResult s = strip_memo<COPULA>(P, S, pt, L, parity, use_memo, k < MEMO_PER_ALPHA - 1, memo_visible, memo_n, a, b,
-                                                         mid, cm, cl, ch, stack ? cl : cm, stack ? cm : ch, poison_mode);
+                                                         mid, cm, cl, ch, stack ? cl : cm, stack ? cm : ch, poison_mode, rm);
                 ncell += s.cells;
                 R = (a == prev_upper) ? R + s.mass : R - s.mass;  // adjust_integral (:241-246)
                 if (R == 0.0) zer |= 1u << k;
                 stack = R < alpha;                                 // :298
                 if (stack) { dec |= 1u << k; lo = mid; u16* t = cl; cl = cm; cm = t; }
                 else       { hi = mid;       u16* t = ch; ch = cm; cm = t; }
+                rows.open &= ~(stack ? rows.at_hi : rows.at_lo);   // the bracket continues with the end the boundary sits on
+                rows.at_lo = rows.at_hi = 0u;
                 prev_upper = mid;
+#ifdef CVAR_PROFILE_PHASES
+                if (k >= 10) prof_thin += clock64() - prof_k0;
+#endif
             }
         }
         if (threadIdx.x == 0 && pt.rank == 0) {
@@ -712,6 +935,12 @@ solve_kernel(KernelParams P, const double* __restrict__ day_params, long long T,
             traj[2 * o + 1] = zer;
             if (mass_out) mass_out[o] = R;
             if (cells_out) cells_out[o] = ncell;
+#ifdef CVAR_PROFILE_PHASES
+            traj[2 * o] = (unsigned)((prof_t1 - prof_t0) >> 4);   // stage 0
+            traj[2 * o + 1] = (unsigned)(prof_thin >> 4);         // bisection passes 10..
+            if (mass_out) mass_out[o] = (double)prof_probe;       // probes + bracket set-up
+            if (cells_out) cells_out[o] = (unsigned long long)(clock64() - prof_t0);
+#endif
         }
     }
     // no CTA may retire while a peer can still read its partial sums
@@ -726,24 +955,25 @@ __global__ void __launch_bounds__(CTA_THREADS_LARGE, 1)
 strip_mass_kernel(KernelParams P, const double* __restrict__ day_params, const double* __restrict__ bounds,
                   double* __restrict__ out, unsigned long long* __restrict__ cells_out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const Smem S = carve(smem_raw, P.n, COPULA);
+    const Smem S = carve(smem_raw, P.n, COPULA, P.pow_octaves);
     const long long day = blockIdx.x;
     const int stride = (P.marginal == 0) ? 2 : 2 * P.q;
-    stage0<COPULA>(P, day_params + day * stride, S);
     Live L;
+    L.day_fast = stage0<COPULA>(P, day_params + day * stride, S);
     if (COPULA == 2) {
         L.i_lo = 0; L.i_hi = P.n; L.j_lo = 0; L.j_hi = P.n;
     } else {
         L.i_lo = S.live[0]; L.i_hi = P.n - S.live[1];
         L.j_lo = S.live[2]; L.j_hi = P.n - S.live[3];
     }
+    L.full = L.i_lo == 0 && L.i_hi == P.n && L.j_lo == 0 && L.j_hi == P.n;
     const bool poison_mode = (COPULA != 2) && (P.marginal == 1) && ((P.compat & 4u) != 0);
     int parity = 0;
     const double lo = bounds[2 * day], hi = bounds[2 * day + 1];
     const Part pt = make_part(0, 1, P.n);
     count_rows(P, S, pt, lo, S.c[0], nullptr, nullptr);
     // an inverted pair yields an empty strip (cb <= ca), like the reference's empty np.where
-    const StripResult s = strip_pass<COPULA>(P, S, pt, L, parity, true, hi, S.c[1], nullptr, nullptr, S.c[0], S.c[1], poison_mode);
+    const StripResult s = strip_pass<COPULA>(P, S, pt, L, parity, hi, S.c[1], nullptr, nullptr, S.c[0], S.c[1], poison_mode);
     if (threadIdx.x == 0) {
         out[day] = s.mass;
         if (cells_out) cells_out[day] = s.cells;

@@ -229,6 +229,61 @@ __device__ __forceinline__ double pow_neg_c(double t, double b, const double* __
     return ((pm * pe) * b) * p;
 }
 
+// ----- the same power over the first octaves of t, one lookup ------------------------------------------
+// Almost every cell has a small quadratic form (t < 2^6 on mixture marginals, where the tails are fat).  For
+// t < 2^octaves one table indexed by t's exponent AND interval bits together -- (high word >> 12) - (1023 << 8),
+// 256 entries per octave -- replaces the two lookups and their product:
+//   CVAR_POW_FAST = 1: 8-byte entries  U = r_i^c * 2^(-c e)  (the rounded product of the two table values, so the cell
+//                      is bit-identical to the two-table form); the seed still comes from MUFU.RCP64H;
+//   CVAR_POW_FAST = 2: 16-byte entries {r_i 2^-e, U}: the seed comes with the same load, which also removes the mask,
+//                      the MUFU and the move that zeroes the seed's low word (3 issue slots per cell).
+// Row blocks that reach t >= 2^octaves anywhere on their ranges take the two-table form (warp-uniform choice).
+#ifndef CVAR_POW_FAST
+#define CVAR_POW_FAST 1
+#endif
+constexpr int POW_FAST_MODE = CVAR_POW_FAST;
+constexpr int POW_FAST_MAX_OCTAVES = 8;
+constexpr int POW_FAST_ENTRY_DOUBLES = POW_FAST_MODE == 2 ? 2 : 1;
+
+__global__ void powfast_build_kernel(double c, int octaves, double* __restrict__ tab) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= octaves * POW_MTAB) return;
+    const int e = idx / POW_MTAB, i = idx % POW_MTAB;
+    // the seed exactly as the cell loop obtains it: MUFU.RCP64H of the interval midpoint carrying t's exponent
+    const double mid = __hiloint2double(((1023 + e) << 20) | (i << (20 - POW_BITS)) | (1 << (19 - POW_BITS)), 0);
+    double rs;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(rs) : "d"(mid));
+    const double u = pow(seed_recip(i, POW_BITS), c) * exp2(-c * (double)e);   // == pm * pe of the two-table form
+    if (POW_FAST_MODE == 2) {
+        tab[2 * idx] = rs;
+        tab[2 * idx + 1] = u;
+    } else {
+        tab[idx] = u;
+    }
+}
+
+// b * t^(-c) for 1 <= t < 2^octaves.  `fast_s` is the shared-window address of the table minus the bias of the index
+// (entry size * (1023 << POW_BITS)), so that the shifted high word of t is the byte offset itself.
+template <int DEG>
+__device__ __forceinline__ double pow_neg_c_fast(double t, double b, const double* __restrict__ kc, unsigned fast_s,
+                                                 unsigned seed_mask, unsigned seed_half) {
+    const unsigned hi = (unsigned)__double2hiint(t);
+    double r, u;
+    if (POW_FAST_MODE == 2) {
+        const unsigned off = (hi >> (20 - POW_BITS - 4)) & ~15u;
+        asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(r), "=d"(u) : "r"(fast_s + off));
+    } else {
+        asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(__hiloint2double((int)((hi & seed_mask) | seed_half), 0)));
+        const unsigned off = (hi >> (20 - POW_BITS - 3)) & ~7u;
+        u = lds_f64(fast_s + off);
+    }
+    const double f = fma(t, r, -1.0);
+    double p = kc[DEG];
+#pragma unroll
+    for (int k = DEG - 1; k >= 0; --k) p = fma(p, f, kc[k]);
+    return (u * b) * p;
+}
+
 // ---------------------------------------------------------------------------------------------
 // per-axis-point functions
 // ---------------------------------------------------------------------------------------------
