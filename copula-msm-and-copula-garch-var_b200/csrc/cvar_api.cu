@@ -52,9 +52,12 @@ struct cvar_plan {
     void* d_ws;
     size_t ws_bytes;
     int* d_k;  // [CVAR_MAX_ALPHA] iteration counts
-    // launch-order scratch (keys, indices, sorted copies, cub temp), grown on demand
+    // launch-order scratch (keys, indices, sorted copies, cub temp), sized by cvar_plan_reserve for `chunk_days` days and
+    // never grown inside a *_device call
+    int64_t chunk_days;
     void* d_sched;
     size_t sched_bytes;
+    size_t sort_tmp_bytes;
     double rho_eff;
 };
 
@@ -213,24 +216,39 @@ int best_cta_threads(int kv, size_t smem, int* threads_out, int* resident_out) {
     return 0;
 }
 
-// Days in ascending order of the portfolio-variance proxy (most expensive solves first); nullptr when the
-// batch fits the resident CTA slots anyway.
+size_t sched_layout(int64_t T, size_t b_tmp, size_t* b_key, size_t* b_idx) {
+    *b_key = align256(sizeof(float) * T);
+    *b_idx = align256(sizeof(int) * T);
+    return 2 * *b_key + 2 * *b_idx + align256(b_tmp);
+}
+
+// (Re)allocate the launch-order scratch for chunks of `days` days.  Host-side set-up only: the *_device entry points
+// never allocate, they cut a batch into chunks of at most chunk_days days (each with its own launch order).
+int reserve_chunk(cvar_plan* p, int64_t days) {
+    days = std::max<int64_t>(1, std::min<int64_t>(days, 0x7fffffffLL));
+    if (days <= p->chunk_days) return 0;
+    CU_TRY(cudaStreamSynchronize(p->stream));
+    if (p->d_sched) CU_TRY(cudaFree(p->d_sched));
+    p->d_sched = nullptr;
+    p->chunk_days = 0;
+    size_t b_tmp = 0, b_key, b_idx;
+    CU_TRY(cub::DeviceRadixSort::SortPairs(nullptr, b_tmp, (const float*)nullptr, (float*)nullptr, (const int*)nullptr,
+                                           (int*)nullptr, (int)days, 0, 32, (cudaStream_t)0));
+    p->sort_tmp_bytes = b_tmp;
+    p->sched_bytes = sched_layout(days, b_tmp, &b_key, &b_idx);
+    CU_TRY(cudaMalloc(&p->d_sched, p->sched_bytes));
+    p->chunk_days = days;
+    return 0;
+}
+
+// Days of a chunk in ascending order of the portfolio-variance proxy (most expensive solves first); nullptr when the
+// chunk fits the resident CTA slots anyway.  Works in the scratch reserved for chunk_days days.
 int make_order(cvar_plan* p, const double* d_day, int64_t T, cudaStream_t st, const int** order_out) {
     *order_out = nullptr;
     if (T <= 2LL * p->sm_count * std::max(p->ctas_per_sm, 1)) return 0;
-    const size_t b_key = align256(sizeof(float) * T), b_idx = align256(sizeof(int) * T);
-    size_t b_tmp = 0;
-    CU_TRY(cub::DeviceRadixSort::SortPairs(nullptr, b_tmp, (const float*)nullptr, (float*)nullptr, (const int*)nullptr,
-                                           (int*)nullptr, (int)T, 0, 32, st));
-    b_tmp = align256(b_tmp);
-    const size_t need = 2 * b_key + 2 * b_idx + b_tmp;
-    if (need > p->sched_bytes) {
-        if (p->d_sched) CU_TRY(cudaFree(p->d_sched));
-        p->d_sched = nullptr;
-        p->sched_bytes = 0;
-        CU_TRY(cudaMalloc(&p->d_sched, need));
-        p->sched_bytes = need;
-    }
+    size_t b_key, b_idx;
+    sched_layout(p->chunk_days, p->sort_tmp_bytes, &b_key, &b_idx);
+    size_t b_tmp = p->sort_tmp_bytes;
     char* base = (char*)p->d_sched;
     float* key_in = (float*)base;
     float* key_out = (float*)(base + b_key);
@@ -263,8 +281,8 @@ int cluster_size(const cvar_plan* p, int64_t T) {
 
 template <typename K>
 int launch_clustered(K kernel, int cluster, unsigned grid, unsigned block, size_t smem, cudaStream_t st, KernelParams kp,
-                     const double* d_day, long long T, AlphaSet A, const int* order, unsigned* traj, double* mass,
-                     unsigned long long* cells) {
+                     const double* d_day, long long day0, long long T, AlphaSet A, const int* order, unsigned* traj,
+                     double* mass, unsigned long long* cells) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(block);
@@ -277,23 +295,23 @@ int launch_clustered(K kernel, int cluster, unsigned grid, unsigned block, size_
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    return (int)cudaLaunchKernelEx(&cfg, kernel, kp, d_day, T, A, order, traj, mass, cells);
+    return (int)cudaLaunchKernelEx(&cfg, kernel, kp, d_day, day0, T, A, order, traj, mass, cells);
 }
 
-int launch_solve(cvar_plan* p, const double* d_day, int64_t T, const AlphaSet& A, uint32_t* d_traj, double* d_mass,
-                 unsigned long long* d_cells, cudaStream_t st) {
-    if (T == 0) return 0;
-    const int* order = nullptr;
-    int rc = make_order(p, d_day, T, st, &order);
-    if (rc) return rc;
-    const int cluster = cluster_size(p, T);
-    dim3 grid((unsigned)T), block(launch_threads(p, T));
+int day_stride(const cvar_plan* p) { return p->desc.marginal == CVAR_MARGINAL_SINGLE ? 2 : 2 * p->desc.q; }
+
+int launch_solve_kernel(cvar_plan* p, int cluster, int threads, int64_t units, const double* d_day, int64_t day0, int64_t T,
+                        const AlphaSet& A, const int* order, uint32_t* d_traj, double* d_mass, unsigned long long* d_cells,
+                        cudaStream_t st) {
+    int rc = 0;
+    dim3 grid((unsigned)units), block(threads);
 #define CVAR_LAUNCH_SOLVE(KV)                                                                                              \
     case KV:                                                                                                               \
         if (cluster > 1)                                                                                                   \
-            return launch_clustered(solve_kernel<KV, true>, cluster, (unsigned)(T * cluster), block.x, p->smem_bytes, st, p->kp, \
-                                    d_day, (long long)T, A, order, d_traj, d_mass, d_cells);                              \
-        solve_kernel<KV, false><<<grid, block, p->smem_bytes, st>>>(p->kp, d_day, (long long)T, A, order, d_traj, d_mass, d_cells); \
+            rc = launch_clustered(solve_kernel<KV, true>, cluster, (unsigned)(units * cluster), block.x, p->smem_bytes, st, p->kp, \
+                                  d_day, (long long)day0, (long long)T, A, order, d_traj, d_mass, d_cells);               \
+        else                                                                                                               \
+            solve_kernel<KV, false><<<grid, block, p->smem_bytes, st>>>(p->kp, d_day, (long long)day0, (long long)T, A, order, d_traj, d_mass, d_cells); \
         break;
     switch (p->kernel_variant) {
         CVAR_LAUNCH_SOLVE(0) CVAR_LAUNCH_SOLVE(1) CVAR_LAUNCH_SOLVE(2) CVAR_LAUNCH_SOLVE(3) CVAR_LAUNCH_SOLVE(4) CVAR_LAUNCH_SOLVE(5)
@@ -301,7 +319,25 @@ int launch_solve(cvar_plan* p, const double* d_day, int64_t T, const AlphaSet& A
         default: return CVAR_ERR_COPULA;
     }
 #undef CVAR_LAUNCH_SOLVE
+    if (rc) return rc;
     return (int)cudaGetLastError();
+}
+
+// A batch runs as chunks of at most chunk_days days (the size of the launch-order scratch): order, solve kernel, on `st`.
+// (Tried and left out: running the cheapest ~20 % of a chunk -- the last CTAs of the launch order -- as 2-CTA clusters in a
+// second kernel on another stream, so that the tail of the launch is made of shorter units.  c3: 1.78 -> 1.82-1.91 ms for
+// 100-400 tail days; the cluster barrier per strip and the second axis stage cost more than the idle SMs of the tail.)
+int launch_solve(cvar_plan* p, const double* d_day, int64_t T, const AlphaSet& A, uint32_t* d_traj, double* d_mass,
+                 unsigned long long* d_cells, cudaStream_t st) {
+    for (int64_t c0 = 0; c0 < T; c0 += p->chunk_days) {
+        const int64_t Tc = std::min(p->chunk_days, T - c0);
+        const int* order = nullptr;
+        int rc = make_order(p, d_day + c0 * day_stride(p), Tc, st, &order);
+        if (rc) return rc;
+        rc = launch_solve_kernel(p, cluster_size(p, Tc), launch_threads(p, Tc), Tc, d_day, c0, T, A, order, d_traj, d_mass, d_cells, st);
+        if (rc) return rc;
+    }
+    return 0;
 }
 
 int launch_strip(cvar_plan* p, const double* d_day, int64_t T, const double* d_bounds, double* d_out,
@@ -334,8 +370,6 @@ int launch_finalize(cvar_plan* p, const uint32_t* d_traj, int64_t T, int32_t n_a
     }
     return 0;
 }
-
-int day_stride(const cvar_plan* p) { return p->desc.marginal == CVAR_MARGINAL_SINGLE ? 2 : 2 * p->desc.q; }
 
 }  // namespace
 
@@ -462,7 +496,9 @@ int cvar_plan_create(const cvar_desc_t* desc, const double* x, const double* dx,
         int th0 = 0, res0 = 0;
         rc = best_cta_threads(p->kernel_variant, p->smem_bytes, &th0, &res0);
         if (rc) { delete p; return rc; }
-        for (int oct = want; oct >= 1; --oct) {
+        // fewer than four octaves (t < 16) catch too few rows to pay for the per-row range check (measured on c2: n = 1024
+        // has room for two octaves next to four resident CTAs and runs 1 % slower with them than without)
+        for (int oct = want; oct >= (std::getenv("CVAR_POW_OCTAVES") ? 1 : 4); --oct) {
             const size_t bytes = smem_bytes_for(n, p->kernel_variant, oct);
             if (bytes > (size_t)prop.sharedMemPerBlockOptin) continue;
             int th = 0, res = 0;
@@ -566,6 +602,7 @@ int cvar_plan_create(const cvar_desc_t* desc, const double* x, const double* dx,
     PLAN_TRY(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
     PLAN_TRY(cudaEventCreate(&p->ev0));
     PLAN_TRY(cudaEventCreate(&p->ev1));
+
     PLAN_TRY(cudaMalloc(&p->d_x, sizeof(double) * n));
     PLAN_TRY(cudaMalloc(&p->d_dx, sizeof(double) * n));
     PLAN_TRY(cudaMalloc(&p->d_k, sizeof(int) * CVAR_MAX_ALPHA));
@@ -689,6 +726,11 @@ int cvar_plan_create(const cvar_desc_t* desc, const double* x, const double* dx,
         default: break;
     }
 #undef CVAR_CLUSTER_OCC
+    {   // launch-order scratch for the default chunk; cvar_plan_reserve (or a *_host call) sizes it for larger batches
+        int64_t days = 65536;
+        if (const char* env = std::getenv("CVAR_CHUNK_DAYS")) days = std::max(1LL, std::atoll(env));
+        PLAN_TRY((cudaError_t)reserve_chunk(p, days));
+    }
 #undef PLAN_TRY
     *out = p;
     return CVAR_OK;
@@ -718,6 +760,13 @@ int cvar_plan_destroy(cvar_plan_t* p) {
     return CVAR_OK;
 }
 
+int cvar_plan_reserve(cvar_plan_t* p, int64_t days) {
+    if (!p) return CVAR_ERR_NULL;
+    if (days < 0) return CVAR_ERR_SIZE;
+    DeviceGuard guard(p->device);
+    return reserve_chunk(p, days);
+}
+
 int cvar_plan_get_info(const cvar_plan_t* p, cvar_plan_info_t* info) {
     if (!p || !info) return CVAR_ERR_NULL;
     info->device = p->device;
@@ -730,6 +779,8 @@ int cvar_plan_get_info(const cvar_plan_t* p, cvar_plan_info_t* info) {
     info->last_kernel_ms = p->last_kernel_ms;
     info->kernel_variant = p->kernel_variant;
     info->cluster4_capacity = p->max_clusters[4];
+    info->pow_octaves = p->kp.pow_octaves;
+    info->chunk_days = p->chunk_days;
     return CVAR_OK;
 }
 
@@ -819,6 +870,7 @@ int cvar_solve_host(cvar_plan_t* p, const double* day_params, int64_t T, const d
         for (int i = 0; i < n_alpha; ++i)
             if (forced[i] > p->kp.max_iter) return CVAR_ERR_PARAM;
     DeviceGuard guard(p->device);
+    { int rr = reserve_chunk(p, T); if (rr) return rr; }
     const size_t na = (size_t)n_alpha;
     const size_t b_day = align256(sizeof(double) * T * day_stride(p));
     const size_t b_trj = align256(sizeof(uint32_t) * 2 * T * na);

@@ -172,10 +172,92 @@ __device__ __forceinline__ Smem carve(unsigned char* base, int n, int kv, int po
 // ---------------------------------------------------------------------------------------------
 // stage 0: per-axis quantities
 // ---------------------------------------------------------------------------------------------
+// One axis point of one asset: the two doubles the cell loop wants for it (reference:
+// integration_functions/*_integration_function.py, copulas/*/*.py).
+//   asset 1 (inner axis, the columns):  first = scaled copula quantile (Plackett: u), second = column weight
+//   asset 0 (outer axis, the rows):     first = quantile / u,                         second = row weight
+// `dead` is set to 1 (lower end) or 2 (upper end) when u saturated to exactly 0 or 1, where the reference's copula
+// density is NaN (Q5/Q10); such points carry zero weight and are counted into the day's live window.
+template <int COPULA>
+__device__ __forceinline__ void axis_point(const KernelParams& P, const double* __restrict__ dayp, int d, int i,
+                                           double& first, double& second, int& dead) {
+    const int n = P.n, q = P.q;
+    const double xi = P.x[i], dxi = P.dx[i];
+    double u, a;
+    dead = 0;
+    if (P.marginal == 0) {
+        // garch_integration_function.py:27-38  (u = Phi(x/sigma), pdf = phi(x/sigma)/sigma)
+        const double sg = dayp[d];
+        const double z = __ddiv_rn(xi, sg);
+        u = phi_via_erf(z);
+        a = (CVAR_INV_SQRT_2PI * exp(-0.5 * z * z) / sg) * dxi;
+    } else {
+        // msm_integration_function.py:32-36 (cdf mixture) and create_grids.py:121,143 (pdf mixture with the vol
+        // states of the OTHER asset when the Q3 compat bit is set).  The vol states are run constants, so
+        // Phi(x_i / sigma_{a,s}) and N(x_i; 0, sigma_{a,s}) do not depend on the day: they are tabulated once per plan
+        // (state_table_kernel) and a day only forms the two probability-weighted sums per axis point -- q FMAs
+        // instead of q erf + q exp evaluations.
+        const bool swap = (P.compat & 1u) != 0;
+        double su = 0.0, sa = 0.0;
+        const double* pr = dayp + d * q;
+        const double* cdf_t = P.state_cdf + (size_t)d * q * n + i;
+        const double* pdf_t = P.state_pdf + (size_t)(swap ? (1 - d) : d) * q * n + i;
+        for (int s = 0; s < q; ++s) {
+            const double p = pr[s];
+            su += p * cdf_t[(size_t)s * n];
+            sa += p * pdf_t[(size_t)s * n];
+        }
+        u = su;
+        a = dxi * sa;
+    }
+    if (COPULA == 2) {
+        first = u;
+        second = a;
+        return;
+    }
+    double y = COPULA == 0 ? normcdfinv(u) : t_quantile_table(P.tq_table, P.nu, P.tq_tail_lc, u);
+    if (!isfinite(y)) {  // u == 0 or u == 1
+        dead = y < 0.0 ? 1 : 2;
+        y = 0.0;
+        a = 0.0;
+    }
+    // quantiles beyond ~1e9 (u below ~1e-19 even at nu = 2; such u only arise from mixture weights far below 1e-10)
+    // are clamped so that the cell's power table never needs an exponent above 2^63; every factor of the cell is
+    // formed from the clamped value, so the cell stays a density value of the same tail (it changes by a power of the
+    // clamp ratio on a region whose total mass is below 1e-19)
+    if (kv_pow_degree(COPULA) > 0) y = copysign(fmin(fabs(y), P.y_max), y);
+    if (COPULA == 0) {
+        if (d == 1) {
+            first = P.g_in_scale * y;
+            second = fmax(log2(a), -1100.0);
+        } else {
+            first = P.g_out_scale * y;
+            second = a * P.g_const * exp(0.5 * y * y);
+        }
+    } else {
+        const double hp = 0.5 * (P.nu + 1.0);
+        const double c = 1.0 + y * y / P.nu;
+        if (d == 1) {
+            first = P.g_in_scale * y;
+            if (kv_pow_degree(COPULA) > 0)   // the power variants multiply by the column weight instead of adding its log
+                second = a * exp2(hp * log2(c));
+            else
+                second = fmax(fmax(log2(a), -1100.0) + hp * log2(c), -1100.0);
+        } else {
+            first = y;   // the row derives m0 = g_out_scale * y0 and c0 = 1 + y0^2 / nu when it is loaded
+            second = a * P.g_const * exp2(hp * log2(c));
+        }
+    }
+}
+
+// Stage 0 of a solve: the day's axis arrays and the plan's lookup tables go to shared memory.  (Measured: running this
+// stage as a separate, fully parallel kernel per batch that hands the arrays over through HBM is NOT faster -- inside
+// the solve kernel its latency hides behind the cell loops of the SM's other resident CTA, while the hand-over adds a
+// launch and 32 n bytes of traffic per day: c3 +1 %, c4 +2 %, c1 +15 %.)
 // Returns true when every cell of the day has a quadratic form below pow_fast_limit (Student-t power variants).
 template <int COPULA>
 __device__ bool stage0(const KernelParams& P, const double* __restrict__ dayp, const Smem& S) {
-    const int n = P.n, q = P.q;
+    const int n = P.n;
     if (threadIdx.x < 4) S.live[threadIdx.x] = 0;
     if (COPULA == KV_STUDENT)
         for (int k = threadIdx.x; k < LOGTAB_SIZE; k += blockDim.x) S.ltab[k] = P.logtab[k];
@@ -186,81 +268,17 @@ __device__ bool stage0(const KernelParams& P, const double* __restrict__ dayp, c
     if (kv_pow_degree(COPULA) > 0 && POW_FAST_MODE > 0)
         for (int k = threadIdx.x; k < P.pow_octaves * POW_MTAB * POW_FAST_ENTRY_DOUBLES; k += blockDim.x) S.pfast[k] = P.powfast[k];
     __syncthreads();
-    const bool swap = (P.compat & 1u) != 0;
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        const double xi = P.x[i], dxi = P.dx[i];
-        S.xs[i] = xi;
-        double u[2], a[2];
-        if (P.marginal == 0) {
-            // garch_integration_function.py:27-38  (u = Phi(x/sigma), pdf = phi(x/sigma)/sigma)
-#pragma unroll
-            for (int d = 0; d < 2; ++d) {
-                const double sg = dayp[d];
-                const double z = __ddiv_rn(xi, sg);
-                u[d] = phi_via_erf(z);
-                a[d] = (CVAR_INV_SQRT_2PI * exp(-0.5 * z * z) / sg) * dxi;
-            }
-        } else {
-            // msm_integration_function.py:32-36 (cdf mixture) and create_grids.py:121,143 (pdf mixture
-            // with the vol states of the OTHER asset when the Q3 compat bit is set).  The vol states are run
-            // constants, so Phi(x_i / sigma_{a,s}) and N(x_i; 0, sigma_{a,s}) do not depend on the day: they
-            // are tabulated once per plan (state_table_kernel) and a day only forms the two probability-
-            // weighted sums per axis point -- q FMAs instead of q erf + q exp evaluations.
-#pragma unroll
-            for (int d = 0; d < 2; ++d) {
-                double su = 0.0, sa = 0.0;
-                const double* pr = dayp + d * q;
-                const double* cdf_t = P.state_cdf + (size_t)d * q * n + i;
-                const double* pdf_t = P.state_pdf + (size_t)(swap ? (1 - d) : d) * q * n + i;
-                for (int s = 0; s < q; ++s) {
-                    const double p = pr[s];
-                    su += p * cdf_t[(size_t)s * n];
-                    sa += p * pdf_t[(size_t)s * n];
-                }
-                u[d] = su;
-                a[d] = dxi * sa;
-            }
-        }
-        if (COPULA == 2) {
-            S.in[i] = make_double2(u[1], a[1]);
-            S.out0[i] = u[0];
-            S.out1[i] = a[0];
-        } else {
-            double y[2];
-#pragma unroll
-            for (int d = 0; d < 2; ++d) {
-                if (COPULA == 0)
-                    y[d] = normcdfinv(u[d]);
-                else
-                    y[d] = t_quantile_table(P.tq_table, P.nu, P.tq_tail_lc, u[d]);
-                if (!isfinite(y[d])) {  // u == 0 or u == 1: the reference's density is NaN there (Q5/Q10)
-                    atomicAdd(&S.live[2 * d + (y[d] < 0.0 ? 0 : 1)], 1);
-                    y[d] = 0.0;
-                    a[d] = 0.0;
-                }
-                // quantiles beyond ~1e9 (u below ~1e-19 even at nu = 2; such u only arise from mixture weights far
-                // below 1e-10) are clamped so that the cell's power table never needs an exponent above 2^63; every
-                // factor of the cell is formed from the clamped value, so the cell stays a density value of the same
-                // tail (it changes by a power of the clamp ratio on a region whose total mass is below 1e-19)
-                if (kv_pow_degree(COPULA) > 0) y[d] = copysign(fmin(fabs(y[d]), P.y_max), y[d]);
-            }
-            const double l1 = fmax(log2(a[1]), -1100.0);
-            if (COPULA == 0) {
-                S.in[i] = make_double2(P.g_in_scale * y[1], l1);
-                S.out0[i] = P.g_out_scale * y[0];
-                S.out1[i] = a[0] * P.g_const * exp(0.5 * y[0] * y[0]);
-            } else {
-                const double hp = 0.5 * (P.nu + 1.0);
-                const double c1 = 1.0 + y[1] * y[1] / P.nu;
-                const double c0 = 1.0 + y[0] * y[0] / P.nu;
-                if (kv_pow_degree(COPULA) > 0)   // the power variants multiply by the column weight instead of adding its log
-                    S.in[i] = make_double2(P.g_in_scale * y[1], a[1] * exp2(hp * log2(c1)));
-                else
-                    S.in[i] = make_double2(P.g_in_scale * y[1], fmax(l1 + hp * log2(c1), -1100.0));
-                S.out0[i] = y[0];   // the row derives m0 = g_out_scale * y0 and c0 = 1 + y0^2 / nu when it is loaded
-                S.out1[i] = a[0] * P.g_const * exp2(hp * log2(c0));
-            }
-        }
+        S.xs[i] = P.x[i];
+        double f0, s0, f1, s1;
+        int dead0, dead1;
+        axis_point<COPULA>(P, dayp, 0, i, f0, s0, dead0);
+        axis_point<COPULA>(P, dayp, 1, i, f1, s1, dead1);
+        S.in[i] = make_double2(f1, s1);
+        S.out0[i] = f0;
+        S.out1[i] = s0;
+        if (dead0) atomicAdd(&S.live[dead0 - 1], 1);
+        if (dead1) atomicAdd(&S.live[2 + dead1 - 1], 1);
     }
     __syncthreads();
     if (kv_pow_degree(COPULA) > 0 && POW_FAST_MODE > 0) {
@@ -389,31 +407,13 @@ __device__ __forceinline__ int count_row(const KernelParams& P, const Smem& S, d
     return max(k, P.cmin);
 }
 
-// Rows whose bracket [lo, hi] has closed (no grid point left between the two boundaries) can never move again during
-// the bisection of the current alpha.  Every thread keeps one bit per owned row: closed rows are not even looked at
-// any more (their boundary entries go stale and are never read), and a round none of whose 32 rows is open costs
-// one warp vote.  By the tenth step nine rows in ten are closed.
-//   open: bit m set = the row of round m may still move;  at_lo / at_hi: the boundary found in the current pass
-//   equals the lower / upper end of the row's bracket, so the row closes if the bracket continues with that end.
-struct RowMask {
-    unsigned open, at_lo, at_hi;
-};
-
 // ctarget[i] = count_row(q) for every outer row this thread owns
 __device__ __forceinline__ void count_rows(const KernelParams& P, const Smem& S, const Part& pt, double q, u16* ctarget,
-                                           const u16* slo, const u16* shi, RowMask* rm = nullptr) {
+                                           const u16* slo, const u16* shi) {
     const int n = P.n;
     for (int m = 0; m < owned_rounds(pt, n); ++m) {
         const int i = owned_row(pt, m);
-        if (i < n && (!rm || ((rm->open >> m) & 1u))) {
-            const int lo = slo ? (int)slo[i] : 0, hi = shi ? (int)shi[i] : n;
-            const int k = count_row(P, S, q, i, lo, hi);
-            ctarget[i] = (u16)k;
-            if (rm) {
-                if (k == lo) rm->at_lo |= 1u << m;
-                if (k == hi) rm->at_hi |= 1u << m;
-            }
-        }
+        if (i < n) ctarget[i] = (u16)count_row(P, S, q, i, slo ? (int)slo[i] : 0, shi ? (int)shi[i] : n);
     }
 }
 
@@ -471,6 +471,9 @@ struct RowStudentPow {  // Student-t: W = rowfac * A1[j] * ( c0 + (y1'[j] - m0)^
     __device__ __forceinline__ void load(const KernelParams& P, const Smem& S, int i) {
         const double y0 = S.out0[i];
         m0 = P.g_out_scale * y0;
+#ifndef CVAR_NO_OPAQUE_M0
+        asm volatile("" : "+d"(m0));   // keep the product: folded into the cells' a - m0 it costs a constant load per trip
+#endif
         c0 = fma(y0 * y0, P.inv_nu, 1.0);
         fac = S.out1[i];
     }
@@ -587,109 +590,38 @@ __device__ __forceinline__ StripResult block_reduce(const Smem& S, const Part& p
 // One strip of the bisection.
 //
 // Every thread owns a fixed set of outer rows (owned_row) for the whole solve: it finds the row's new boundary
-// index by an exact search (when q_new is given); the row's cells [a, b) are then summed in one of two ways.
-//
-//  * Column sweep (the 32 rows of a warp's block all hold cells and overlap in at least BCAST_MIN_BODY columns).
-//    The lanes of a GROUP of CVAR_BCAST_GROUP adjacent rows read the SAME column in the same trip -- one 16-byte
-//    shared-memory word per group, a broadcast -- and the groups are skewed against each other by the shift of
-//    their rows' ranges, so that all of them start and end together.  A warp-wide column load then costs ONE
-//    shared-memory wavefront (the groups' words are steered into distinct banks) instead of the four of 32
-//    distinct words, and the lanes of a group meet the lookup tables of the cell at neighbouring entries.  The
-//    shared-memory data pipe was the binding unit of the lane-per-row walk (ncu: 7.6 wavefronts per warp-cell,
-//    pipe saturated inside the loop); the sweep needs about three.
-//  * Lane-per-row walk for what is left: the columns of a row outside the common window (a ramp of at most
-//    ~GROUP columns per end), blocks at the edge of the strip and the thin strips of the late iterations.
-//
+// index by an exact search (when q_new is given), then walks the row's cells [a, b) itself with
+// CELLS_IN_FLIGHT independent cells per trip.  Adjacent lanes own adjacent rows, whose ranges are shifted
+// by about one column, so the 16-byte shared-memory loads of a warp fall on consecutive addresses.
 // There is no per-strip barrier besides the one inside the block reduction, and the boundary arrays are
 // only ever touched by their owning thread.
-//   bound arrays: ca == nullptr means the constant lower end cmin; cnew (may alias ca or cb) receives
-//   count(q_new) searched inside [slo[i], shi[i]] before the row is summed.
-#ifndef CVAR_BCAST_GROUP
-#define CVAR_BCAST_GROUP 0   // 0: lane-per-row walk only; 2 / 4 / 8 / 16: skewed groups; 32: the whole warp on one column
-#endif
-#ifndef CVAR_BCAST_MIN_ROW
-#define CVAR_BCAST_MIN_ROW 16   // shortest row of the block below which the sweep is not even attempted
-#endif
-#ifndef CVAR_PREFETCH
-#define CVAR_PREFETCH 1      // sweep: the next trip's columns are loaded before this trip's cells are evaluated
-#endif
-constexpr int BCAST_GROUP = CVAR_BCAST_GROUP;
-constexpr int BCAST_MIN_BODY = 8;
+//
+// (Tried in round 2 and left out, see DESIGN.md section 10: a warp-synchronous "column sweep" in which groups of 2 / 4 / 8 /
+// 32 adjacent rows read the same column per trip -- one shared-memory wavefront per warp load instead of four, 10 % faster
+// in an isolated loop (tools/micro/cell_loop.cu) -- lost 2-4 % in the kernel: the rows of a group start and end at
+// different columns, and the ramps at both ends plus the warp votes per row block cost more than the wavefronts save.)
 
-// Sum of the cells [s, e) of this lane's row.  All 32 lanes of the warp must call it (warp votes / shuffles
-// inside); lanes without cells pass s == e.
+// Sum of the cells [s, e) of one row.
 template <int COPULA, bool FAST>
-__device__ __forceinline__ double walk_block(const KernelParams& P, const Smem& S, const Row<COPULA>& row, int s, int e) {
+__device__ __forceinline__ double walk_row(const KernelParams& P, const Smem& S, const Row<COPULA>& row, int s, int e) {
     constexpr int CIF = CellsInFlight<COPULA>::value;
-    constexpr unsigned FULL = 0xffffffffu;
-    constexpr int G = BCAST_GROUP > 0 ? BCAST_GROUP : 32;
 #ifdef CVAR_EXPERIMENT_NO_CELLS   // timing experiment: everything but the cell loops (results are meaningless)
     return 1e-9 * (double)(e - s);
 #endif
     double acc[CIF];
 #pragma unroll
     for (int c = 0; c < CIF; ++c) acc[c] = 0.0;
-    int left_end = s, right_begin = s;   // lane-per-row segments [s, left_end) and [right_begin, e)
-    if (BCAST_GROUP > 0 && __all_sync(FULL, e - s >= CVAR_BCAST_MIN_ROW)) {
-        int off = 0;   // this lane reads column (trip - off)
-        if (G < 32) {
-            constexpr int NG = 32 / G;
-            const int lane = threadIdx.x & 31, g = lane / G;
-            // align the groups' first columns; then make the offsets distinct modulo the number of groups, which puts
-            // the groups' 16-byte words into different banks
-            off = __shfl_sync(FULL, s, 0) - __shfl_sync(FULL, s, lane & ~(G - 1));
-            if (NG <= 8)
-                off += (g - off) & (NG - 1);
-            else   // 16 pairs: their words must fall on every 16-byte bank group exactly twice (offsets 2g + g/4 modulo 8)
-                off += ((2 * g + (g >> 2)) - off) & 7;
-        }
-        const int t0 = __reduce_max_sync(FULL, s + off);
-        const int t1 = __reduce_min_sync(FULL, e + off);
-        if (t1 - t0 >= BCAST_MIN_BODY) {
-            const int trips = (t1 - t0) / CIF;
-            const double2* col = S.in + (t0 - off);
-            if (CVAR_PREFETCH) {
-                double2 v[CIF];
+    int j = s;
+    for (; j + CIF <= e; j += CIF) {
+        double2 v[CIF];
 #pragma unroll
-                for (int c = 0; c < CIF; ++c) v[c] = col[c];
-                for (int k = 0; k < trips; ++k) {
-                    col += CIF;
-                    double2 w[CIF];   // the last trip reads CIF columns past the window: still inside the shared arrays, unused
+        for (int c = 0; c < CIF; ++c) v[c] = S.in[j + c];
 #pragma unroll
-                    for (int c = 0; c < CIF; ++c) w[c] = col[c];
-#pragma unroll
-                    for (int c = 0; c < CIF; ++c) acc[c] = row.template add_cell<FAST>(P, S, v[c].x, v[c].y, acc[c]);
-#pragma unroll
-                    for (int c = 0; c < CIF; ++c) v[c] = w[c];
-                }
-            } else {
-                for (int k = 0; k < trips; ++k, col += CIF) {
-                    double2 v[CIF];
-#pragma unroll
-                    for (int c = 0; c < CIF; ++c) v[c] = col[c];
-#pragma unroll
-                    for (int c = 0; c < CIF; ++c) acc[c] = row.template add_cell<FAST>(P, S, v[c].x, v[c].y, acc[c]);
-                }
-            }
-            left_end = t0 - off;
-            right_begin = t0 - off + trips * CIF;
-        }
+        for (int c = 0; c < CIF; ++c) acc[c] = row.template add_cell<FAST>(P, S, v[c].x, v[c].y, acc[c]);
     }
-#pragma unroll 1
-    for (int seg = (BCAST_GROUP > 0 ? 0 : 1); seg < 2; ++seg) {
-        int j = seg ? right_begin : s;
-        const int je = seg ? e : left_end;
-        for (; j + CIF <= je; j += CIF) {
-            double2 v[CIF];
-#pragma unroll
-            for (int c = 0; c < CIF; ++c) v[c] = S.in[j + c];
-#pragma unroll
-            for (int c = 0; c < CIF; ++c) acc[c] = row.template add_cell<FAST>(P, S, v[c].x, v[c].y, acc[c]);
-        }
-        for (; j < je; ++j) {
-            const double2 v = S.in[j];
-            acc[0] = row.template add_cell<FAST>(P, S, v.x, v.y, acc[0]);
-        }
+    for (; j < e; ++j) {
+        const double2 v = S.in[j];
+        acc[0] = row.template add_cell<FAST>(P, S, v.x, v.y, acc[0]);
     }
     double rowsum = acc[0];
 #pragma unroll
@@ -703,8 +635,7 @@ __device__ __forceinline__ double walk_block(const KernelParams& P, const Smem& 
 template <int COPULA>
 __device__ StripResult strip_pass(const KernelParams& P, const Smem& S, const Part& pt, const Live& L, int& parity,
                                   double q_new, u16* cnew, const u16* slo, const u16* shi, const u16* ca,
-                                  const u16* cb, bool poison_mode, RowMask* rm = nullptr) {
-    constexpr unsigned FULL = 0xffffffffu;
+                                  const u16* cb, bool poison_mode) {
     const int n = P.n;
     double total = 0.0;
     unsigned cells = 0;
@@ -712,10 +643,8 @@ __device__ StripResult strip_pass(const KernelParams& P, const Smem& S, const Pa
     const bool between = slo && shi && P.w0 > 0.0;   // both bracket ends known and ordered: midpoint search
     for (int m = 0; m < owned_rounds(pt, n); ++m) {
         const int i = owned_row(pt, m);
-        const bool open = i < n && (!rm || ((rm->open >> m) & 1u));
-        if (rm && !__any_sync(FULL, open)) continue;   // the 32 rows of this block are closed
         int s = 0, e = 0;
-        if (open) {
+        if (i < n) {
             const double xi = S.xs[i];
             const int lo = slo ? (int)slo[i] : 0, hi = shi ? (int)shi[i] : n;
             int k = lo;
@@ -728,10 +657,6 @@ __device__ StripResult strip_pass(const KernelParams& P, const Smem& S, const Pa
                 e = cb == cnew ? k : cb == slo ? lo : cb == shi ? hi : (int)cb[i];
             }
             cnew[i] = (u16)k;
-            if (rm) {
-                if (k == lo) rm->at_lo |= 1u << m;
-                if (k == hi) rm->at_hi |= 1u << m;
-            }
 #ifdef CVAR_DEBUG_ASSERT
             if (s < 0 || e > n || k > n) __trap();
 #endif
@@ -749,25 +674,24 @@ __device__ StripResult strip_pass(const KernelParams& P, const Smem& S, const Pa
                 }
             }
         }
-        const bool act = e > s;
-        if (!__any_sync(FULL, act)) continue;
-        if (!act) s = e = 0;
+        if (e <= s) continue;
         Row<COPULA> row;
-        row.load(P, S, act ? i : 0);
+        row.load(P, S, i);
         double rowsum;
         bool fast = false;
         if (kv_pow_degree(COPULA) > 0 && POW_FAST_MODE > 0 && P.pow_octaves > 0) {
+            // The quadratic form is convex along the row: check the two ends of this strip's range.  The lanes walking
+            // rows together take the same form of the cell (both forms give the same bits; a warp split between the two
+            // loops would run them one after the other).
             fast = L.day_fast;
-            if (!fast) {   // the quadratic form is convex along the row: check the two ends of this strip's range
-                const double tmax = act ? fmax(row.quad_form(S.in[s].x), row.quad_form(S.in[e - 1].x)) : 0.0;
-                fast = !__any_sync(FULL, !(tmax < P.pow_fast_limit));
-            }
+            if (!fast)
+                fast = !__any_sync(__activemask(), !(fmax(row.quad_form(S.in[s].x), row.quad_form(S.in[e - 1].x)) < P.pow_fast_limit));
         }
         if (kv_pow_degree(COPULA) > 0 && POW_FAST_MODE > 0 && fast)
-            rowsum = walk_block<COPULA, true>(P, S, row, s, e);
+            rowsum = walk_row<COPULA, true>(P, S, row, s, e);
         else
-            rowsum = walk_block<COPULA, false>(P, S, row, s, e);
-        if (act) total = fma(row.fac, rowsum, total);
+            rowsum = walk_row<COPULA, false>(P, S, row, s, e);
+        total = fma(row.fac, rowsum, total);
     }
     StripResult r = block_reduce(S, pt, parity, total, cells, poison && poison_mode);
     if (r.poisoned) r.mass = NAN;
@@ -782,12 +706,12 @@ __device__ __forceinline__ StripResult strip_memo(const KernelParams& P, const S
                                                   bool use_memo, bool remember, int memo_visible, int& memo_n,
                                                   double a, double b,
                                                   double q_new, u16* cnew, const u16* slo, const u16* shi,
-                                                  const u16* ca, const u16* cb, bool poison_mode, RowMask* rm = nullptr) {
+                                                  const u16* ca, const u16* cb, bool poison_mode) {
     if (use_memo) {
         for (int k = 0; k < memo_visible; ++k) {
             const double* e = S.memo + 4 * k;
             if (e[0] == a && e[1] == b) {
-                count_rows(P, S, pt, q_new, cnew, slo, shi, rm);  // the boundary indices are still needed downstream
+                count_rows(P, S, pt, q_new, cnew, slo, shi);  // the boundary indices are still needed downstream
                 StripResult r;
                 r.mass = e[2];
                 r.cells = (unsigned)e[3];
@@ -796,7 +720,7 @@ __device__ __forceinline__ StripResult strip_memo(const KernelParams& P, const S
             }
         }
     }
-    const StripResult r = strip_pass<COPULA>(P, S, pt, L, parity, q_new, cnew, slo, shi, ca, cb, poison_mode, rm);
+    const StripResult r = strip_pass<COPULA>(P, S, pt, L, parity, q_new, cnew, slo, shi, ca, cb, poison_mode);
     if (use_memo && remember && memo_n < MEMO_SIZE) {
         if (threadIdx.x == 0) {
             double* e = S.memo + 4 * memo_n;
@@ -814,7 +738,7 @@ __device__ __forceinline__ StripResult strip_memo(const KernelParams& P, const S
 // stage 0 for itself, owns a share of the outer rows and sees the same strip masses, hence takes the same decisions).
 template <int COPULA, bool CLUSTER>
 __global__ void __launch_bounds__(CTA_THREADS_LARGE, 1)
-solve_kernel(KernelParams P, const double* __restrict__ day_params, long long T, AlphaSet A,
+solve_kernel(KernelParams P, const double* __restrict__ day_params, long long day0, long long T, AlphaSet A,
              const int* __restrict__ order, unsigned* __restrict__ traj, double* __restrict__ mass_out,
              unsigned long long* __restrict__ cells_out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -825,8 +749,9 @@ solve_kernel(KernelParams P, const double* __restrict__ day_params, long long T,
         pt = make_part((int)cluster.block_rank(), (int)cluster.num_blocks(), P.n);
     }
     // CTAs are dispatched in block-index order; `order` lists the days most expensive first (see order_key_kernel)
+    // (the grid covers one chunk of the batch, whose first day is day0; `order` indexes within the chunk)
     const long long unit = blockIdx.x / pt.size;
-    const long long day = order ? order[unit] : unit;
+    const long long day = day0 + (order ? order[unit] : unit);
     const int stride = (P.marginal == 0) ? 2 : 2 * P.q;
 #ifdef CVAR_PROFILE_PHASES   // experiment: thread 0's clock per phase goes out through traj / mass / cells (results are overwritten)
     const long long prof_t0 = clock64();
@@ -901,8 +826,6 @@ solve_kernel(KernelParams P, const double* __restrict__ day_params, long long T,
         }
         bool stack = !(hi == P.second_lo || hi == P.second_hi);  // :160
         unsigned dec = 0, zer = 0;
-        RowMask rows = {0xffffffffu, 0u, 0u};
-        RowMask* rm = owned_rounds(pt, P.n) <= 32 ? &rows : nullptr;
         if (kase != 4) {
 #ifdef CVAR_PROFILE_PHASES
             prof_probe = clock64() - prof_t1;
@@ -914,15 +837,13 @@ solve_kernel(KernelParams P, const double* __restrict__ day_params, long long T,
                 const double mid = (lo + hi) / 2;
                 const double a = stack ? lo : mid, b = stack ? mid : hi;
                 const StripResult s = strip_memo<COPULA>(P, S, pt, L, parity, use_memo, k < MEMO_PER_ALPHA - 1, memo_visible, memo_n, a, b,
-                                                         mid, cm, cl, ch, stack ? cl : cm, stack ? cm : ch, poison_mode, rm);
+                                                         mid, cm, cl, ch, stack ? cl : cm, stack ? cm : ch, poison_mode);
                 ncell += s.cells;
                 R = (a == prev_upper) ? R + s.mass : R - s.mass;  // adjust_integral (:241-246)
                 if (R == 0.0) zer |= 1u << k;
                 stack = R < alpha;                                 // :298
                 if (stack) { dec |= 1u << k; lo = mid; u16* t = cl; cl = cm; cm = t; }
                 else       { hi = mid;       u16* t = ch; ch = cm; cm = t; }
-                rows.open &= ~(stack ? rows.at_hi : rows.at_lo);   // the bracket continues with the end the boundary sits on
-                rows.at_lo = rows.at_hi = 0u;
                 prev_upper = mid;
 #ifdef CVAR_PROFILE_PHASES
                 if (k >= 10) prof_thin += clock64() - prof_k0;

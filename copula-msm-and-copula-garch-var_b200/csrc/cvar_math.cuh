@@ -273,9 +273,11 @@ __device__ __forceinline__ double pow_neg_c_fast(double t, double b, const doubl
         const unsigned off = (hi >> (20 - POW_BITS - 4)) & ~15u;
         asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(r), "=d"(u) : "r"(fast_s + off));
     } else {
-        asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(__hiloint2double((int)((hi & seed_mask) | seed_half), 0)));
-        const unsigned off = (hi >> (20 - POW_BITS - 3)) & ~7u;
-        u = lds_f64(fast_s + off);
+        // the seed word (interval bits kept, midpoint bit set, lower bits clear) shifted down is 8 * index + 4: the byte
+        // offset of the entry needs no mask of its own
+        const unsigned sh = (hi & seed_mask) | seed_half;
+        asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(__hiloint2double((int)sh, 0)));
+        u = lds_f64(fast_s - 4u + (sh >> (20 - POW_BITS - 3)));
     }
     const double f = fma(t, r, -1.0);
     double p = kc[DEG];

@@ -33,6 +33,7 @@ class CvarPlanInfo(C.Structure):
         ("threads_per_cta", C.c_int32), ("smem_bytes_per_cta", C.c_int32),
         ("tq_table_max_rel_err", C.c_double), ("last_kernel_ms", C.c_double),
         ("kernel_variant", C.c_int32), ("cluster4_capacity", C.c_int32),
+        ("pow_octaves", C.c_int32), ("chunk_days", C.c_int64),
     ]
 
 
@@ -51,6 +52,7 @@ _PROTOTYPES = {
     "cvar_plan_create": (C.c_int, [C.POINTER(CvarDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]),
     "cvar_plan_destroy": (C.c_int, [C.c_void_p]),
     "cvar_plan_get_info": (C.c_int, [C.c_void_p, C.POINTER(CvarPlanInfo)]),
+    "cvar_plan_reserve": (C.c_int, [C.c_void_p, C.c_int64]),
     "cvar_strip_mass_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "cvar_strip_mass_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "cvar_solve_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),

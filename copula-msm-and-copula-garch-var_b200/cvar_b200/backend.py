@@ -71,6 +71,7 @@ class VarPlan:
                                   -1 if device is None else int(device), C.byref(handle))
         _lib.check(st, "cvar_plan_create")
         self._h = handle
+        self._reserved = 0
         self.device = self.info().device
 
     # -- lifetime ---------------------------------------------------------------------------
@@ -90,6 +91,17 @@ class VarPlan:
 
     def __exit__(self, *exc):
         self.close()
+
+    def reserve(self, days: int) -> int:
+        """Size the plan's per-chunk device scratch for batches of `days` days (cvar_plan_reserve); returns the chunk size.
+
+        The C `*_device` entry points never allocate: a batch larger than the reserved chunk runs in several chunks.
+        `solve_device` / `strip_mass_device` below reserve for their batch on first use, so that a device-resident
+        batch normally runs as one chunk."""
+        if days > self._reserved:
+            _lib.check(self._lib.cvar_plan_reserve(self._h, int(days)), "cvar_plan_reserve")
+            self._reserved = max(int(days), int(self.info().chunk_days))
+        return int(self.info().chunk_days)
 
     def info(self) -> _lib.CvarPlanInfo:
         info = _lib.CvarPlanInfo()
@@ -115,10 +127,13 @@ class VarPlan:
         _lib.check(st, "cvar_strip_mass_host")
         return (out, cells) if return_cells else out
 
-    def solve(self, day_params, alphas, ptf_mean: float = 0.0, forced_iterations=None, out=None) -> SolveResult:
+    def solve(self, day_params, alphas, ptf_mean: float = 0.0, forced_iterations=None, out=None,
+              details: bool = True) -> SolveResult:
         """All (day, alpha) solves of a batch: `calc_var` for every alpha (calc_var_class.py:95-177).
 
         ``out`` may be a preallocated (n_alpha, T) float64 array (e.g. pinned memory) receiving the VaR levels.
+        ``details=False`` skips the bracket ids and cell counters (`case` and `cells` of the result are None): nothing
+        but the VaR vector and the iteration counts is copied back.
         """
         alphas = _f64(np.atleast_1d(alphas))
         na = alphas.shape[0]
@@ -129,8 +144,8 @@ class VarPlan:
         var = out if out is not None else np.empty((na, T))
         if var.shape != (na, T) or var.dtype != np.float64 or not var.flags.c_contiguous:
             raise ValueError("out must be a C-contiguous float64 array of shape (n_alpha, T)")
-        case = np.empty((na, T), dtype=np.int32)
-        cells = np.empty((na, T), dtype=np.uint64)
+        case = np.empty((na, T), dtype=np.int32) if details else None
+        cells = np.empty((na, T), dtype=np.uint64) if details else None
         iters = np.empty(na, dtype=np.int32)
         forced = None if forced_iterations is None else np.ascontiguousarray(
             np.broadcast_to(np.asarray(forced_iterations, dtype=np.int32), (na,)))
@@ -156,8 +171,10 @@ class VarPlan:
         if t.device.index != self.device:
             raise ValueError(f"{name} lives on cuda:{t.device.index}, the plan on cuda:{self.device}")
 
-    def solve_device(self, day_params, alphas, traj=None, mass=None, cells=None):
-        """Enqueue the solve kernel on torch's current stream. Returns the trajectory tensor (n_alpha, T, 2) int32."""
+    def solve_device(self, day_params, alphas, traj=None, mass=None, cells=None, reserve: bool = True):
+        """Enqueue the solve kernel on torch's current stream. Returns the trajectory tensor (n_alpha, T, 2) int32.
+
+        ``reserve=False`` leaves the plan's chunk size as it is (a larger batch then runs in several chunks)."""
         import torch
 
         self._check_tensor(day_params, torch.float64, "day_params")
@@ -171,6 +188,8 @@ class VarPlan:
             self._check_tensor(mass, torch.float64, "mass")
         if cells is not None:
             self._check_tensor(cells, torch.int64, "cells")
+        if reserve:
+            self.reserve(T)
         stream = torch.cuda.current_stream(day_params.device).cuda_stream
         st = self._lib.cvar_solve_device(self._h, C.c_void_p(day_params.data_ptr()), T, _ptr(alphas), na,
                                          C.c_void_p(traj.data_ptr()),
@@ -209,6 +228,7 @@ class VarPlan:
         T = bounds.shape[0]
         if out is None:
             out = torch.empty((T,), dtype=torch.float64, device=bounds.device)
+        self.reserve(T)
         stream = torch.cuda.current_stream(bounds.device).cuda_stream
         st = self._lib.cvar_strip_mass_device(self._h, C.c_void_p(day_params.data_ptr()), T, C.c_void_p(bounds.data_ptr()),
                                               C.c_void_p(out.data_ptr()), None, C.c_void_p(stream))

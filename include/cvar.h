@@ -130,6 +130,8 @@ typedef struct cvar_plan_info {
                                   table-assisted power cell of degree 5/6/7/8 (picked from nu at plan creation) */
     int32_t cluster4_capacity; /* 4-CTA clusters of the solve kernel that can be resident at once: batches of at most
                                   this many days are split four ways, up to about twice as many two ways (n >= 1024) */
+    int32_t pow_octaves;       /* Student-t power cell: octaves of the quadratic form covered by the one-lookup table */
+    int64_t chunk_days;        /* days per launch of the solve kernel (size of the launch-order scratch, cvar_plan_reserve) */
 } cvar_plan_info_t;
 
 /*
@@ -159,6 +161,14 @@ int cvar_plan_create(const cvar_desc_t* desc, const double* x_host, const double
                      const double* sigma_states_host, int device, cvar_plan_t** plan_out);
 int cvar_plan_destroy(cvar_plan_t* plan);
 int cvar_plan_get_info(const cvar_plan_t* plan, cvar_plan_info_t* info_out);
+/*
+ * Size the plan's launch-order scratch (about 16 bytes per day) for batches of `days` days.  A batch larger than the
+ * reserved chunk still runs, cut into chunks that are ordered and launched one after the other; the default chunk is
+ * 65536 days (CVAR_CHUNK_DAYS).  The `*_host` solve reserves for its own batch; the `*_device` entry points never
+ * allocate, so callers with larger device-resident batches reserve once after plan creation.  Only ever grows;
+ * synchronises the plan's stream when it reallocates.  (No counterpart in the reference.)
+ */
+int cvar_plan_reserve(cvar_plan_t* plan, int64_t days);
 
 /*
  * Strip masses: out[t] = S(bounds[t][0], bounds[t][1]) for day t.

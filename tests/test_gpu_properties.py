@@ -247,3 +247,30 @@ def test_row_boundaries_stay_exact_on_any_axis(backend, axis):
     for k, a in enumerate([0.01, 0.05]):
         tr = vo.calc_var(inp, a)
         assert res.var[k].tobytes() == tr.var.tobytes() and np.array_equal(res.case[k], tr.case)
+
+
+@pytest.mark.gpu
+def test_chunked_batches_equal_single_chunk_batches(monkeypatch):
+    """A batch larger than the plan's reserved chunk (cvar_plan_reserve) is cut into chunks, each with its own axis
+    stage and launch order; decisions, masses and cell counts must not depend on the cut."""
+    import torch
+    from cvar_b200.backend import VarPlan
+    from cvar_b200 import synthetic as syn
+
+    inp, alphas = syn.baseline_config("c2", T=53, n=160)
+    d_day = torch.from_numpy(inp.day_params()).cuda()
+    with VarPlan(inp, device=0) as whole:
+        ref_mass = torch.zeros((2, inp.T), dtype=torch.float64, device="cuda")
+        ref_cells = torch.zeros((2, inp.T), dtype=torch.int64, device="cuda")
+        ref = whole.solve_device(d_day, alphas, mass=ref_mass, cells=ref_cells).cpu().numpy()
+        assert whole.info().chunk_days >= inp.T
+    monkeypatch.setenv("CVAR_CHUNK_DAYS", "7")
+    with VarPlan(inp, device=0) as cut:
+        assert cut.info().chunk_days == 7
+        mass = torch.zeros((2, inp.T), dtype=torch.float64, device="cuda")
+        cells = torch.zeros((2, inp.T), dtype=torch.int64, device="cuda")
+        got = cut.solve_device(d_day, alphas, mass=mass, cells=cells, reserve=False).cpu().numpy()
+        assert cut.info().chunk_days == 7
+    np.testing.assert_array_equal(got, ref)
+    np.testing.assert_array_equal(cells.cpu().numpy(), ref_cells.cpu().numpy())
+    np.testing.assert_array_equal(mass.cpu().numpy(), ref_mass.cpu().numpy())
