@@ -51,7 +51,7 @@ struct cvar_plan {
     // growable workspace of the *_host entry points
     void* d_ws;
     size_t ws_bytes;
-    int* d_k;  // [CVAR_MAX_ALPHA] iteration counts
+    int* d_k;  // [2][CVAR_MAX_ALPHA]: iteration counts, then status words of the last finalize
     // launch-order scratch (keys, indices, sorted copies, cub temp), sized by cvar_plan_reserve for `chunk_days` days and
     // never grown inside a *_device call
     int64_t chunk_days;
@@ -360,7 +360,7 @@ int launch_finalize(cvar_plan* p, const uint32_t* d_traj, int64_t T, int32_t n_a
     FinalizeParams F = p->fp;
     F.ptf_mean = ptf_mean;
     for (int i = 0; i < CVAR_MAX_ALPHA; ++i) F.forced[i] = (forced && i < n_alpha) ? forced[i] : -1;
-    finalize_reduce_kernel<<<n_alpha, 1024, 0, st>>>(F, d_traj, (long long)T, p->d_k);
+    finalize_reduce_kernel<<<n_alpha, 1024, 0, st>>>(F, d_traj, (long long)T, p->d_k, p->d_k + CVAR_MAX_ALPHA);
     CU_TRY(cudaGetLastError());
     const long long total = (long long)T * n_alpha;
     if (total > 0) {
@@ -412,6 +412,7 @@ const char* cvar_strerror(int status) {
         case CVAR_ERR_NO_DEVICE: return "no usable CUDA device (this library has no CPU fallback)";
         case CVAR_ERR_ABI: return "cvar_desc_t struct_size / abi_version mismatch";
         case CVAR_ERR_SMEM: return "grid too large for the shared memory of one SM";
+        case CVAR_ERR_TABLE: return "Student-t quantile table missed its accuracy budget for this nu (plan refused)";
         default: break;
     }
     if (status > 0) return cudaGetErrorString((cudaError_t)status);
@@ -605,7 +606,8 @@ int cvar_plan_create(const cvar_desc_t* desc, const double* x, const double* dx,
 
     PLAN_TRY(cudaMalloc(&p->d_x, sizeof(double) * n));
     PLAN_TRY(cudaMalloc(&p->d_dx, sizeof(double) * n));
-    PLAN_TRY(cudaMalloc(&p->d_k, sizeof(int) * CVAR_MAX_ALPHA));
+    PLAN_TRY(cudaMalloc(&p->d_k, sizeof(int) * 2 * CVAR_MAX_ALPHA));
+    PLAN_TRY(cudaMemsetAsync(p->d_k, 0, sizeof(int) * 2 * CVAR_MAX_ALPHA, p->stream));
     PLAN_TRY(cudaMemcpyAsync(p->d_x, x, sizeof(double) * n, cudaMemcpyHostToDevice, p->stream));
     PLAN_TRY(cudaMemcpyAsync(p->d_dx, dx, sizeof(double) * n, cudaMemcpyHostToDevice, p->stream));
     if (desc->marginal == CVAR_MARGINAL_MIXTURE) {
@@ -646,6 +648,14 @@ int cvar_plan_create(const cvar_desc_t* desc, const double* x, const double* dx,
         cudaFree(d_err);
         PLAN_TRY(ce);
         std::memcpy(&p->tq_err, &bits, sizeof(double));
+        // Accuracy budget of the table: 1e-11 relative keeps a cell weight inside its 1e-13 budget with two decades to
+        // spare at the largest exponent (nu + 2) / 2 the table is used with.  Measured: <= 3e-14 for 2.01 <= nu <= 50.
+        // A degree of freedom for which the table misses it (or whose check produced a NaN) is refused instead of being
+        // solved with an inaccurate quantile.  (Falling back to the iterative routine inside the kernel was measured:
+        // the call costs the solve kernel 6 registers and ~1 % on every Student-t plan.)
+        double budget = 1e-11;
+        if (const char* env = std::getenv("CVAR_TQ_BUDGET")) budget = std::atof(env);   // tests
+        if (!(p->tq_err <= budget)) { cvar_plan_destroy(p); return CVAR_ERR_TABLE; }
         kp.tq_table = p->d_tq_table;
         // table-assisted log2 of the cell loop: constants scaled by -(nu+2)/2
         constexpr double q1p[] = CVAR_LOG2_1P_POLY;
@@ -855,6 +865,23 @@ int cvar_finalize_device(cvar_plan_t* p, const uint32_t* traj, int64_t T, int32_
     if (rc) return rc;
     if (iterations_out)
         CU_TRY(cudaMemcpyAsync(iterations_out, p->d_k, sizeof(int) * n_alpha, cudaMemcpyDeviceToDevice, st));
+    return CVAR_OK;
+}
+
+int cvar_finalize_status_device(cvar_plan_t* p, int32_t* status_out, int32_t n_alpha, void* stream) {
+    if (!p || !status_out) return CVAR_ERR_NULL;
+    if (n_alpha < 1 || n_alpha > CVAR_MAX_ALPHA) return CVAR_ERR_SIZE;
+    DeviceGuard guard(p->device);
+    CU_TRY(cudaMemcpyAsync(status_out, p->d_k + CVAR_MAX_ALPHA, sizeof(int) * n_alpha, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return CVAR_OK;
+}
+
+int cvar_finalize_status_host(cvar_plan_t* p, int32_t* status_out, int32_t n_alpha) {
+    if (!p || !status_out) return CVAR_ERR_NULL;
+    if (n_alpha < 1 || n_alpha > CVAR_MAX_ALPHA) return CVAR_ERR_SIZE;
+    DeviceGuard guard(p->device);
+    CU_TRY(cudaMemcpyAsync(status_out, p->d_k + CVAR_MAX_ALPHA, sizeof(int) * n_alpha, cudaMemcpyDeviceToHost, p->stream));
+    CU_TRY(cudaStreamSynchronize(p->stream));
     return CVAR_OK;
 }
 

@@ -731,6 +731,15 @@ __device__ __forceinline__ StripResult strip_memo(const KernelParams& P, const S
     return r;
 }
 
+// Bit 31 of a solve's first trajectory word: during the bisection a running mass cancelled to rounding noise (twelve or
+// more digits lost) without being exactly 0.  In exact arithmetic such a mass IS 0; whether the reference's sums cancel
+// exactly -- which decides its "every day's mass is 0" exit (calc_var_class.py:293-295) -- depends on the order in which
+// it happened to add the cells.  finalize reports a batch in which every day is in that state (status word below).
+constexpr unsigned TRAJ_FRAGILE_BIT = 0x80000000u;
+constexpr int STATUS_ZERO_EXIT_TAKEN = 1;       // K was cut because every day's running mass was exactly 0 at iteration K
+constexpr int STATUS_ZERO_EXIT_AMBIGUOUS = 2;   // every day's mass was 0 exactly or up to rounding at some iteration: the
+                                                // reference's outcome for this batch depends on its summation order
+
 // ---------------------------------------------------------------------------------------------
 // the solve kernel
 // ---------------------------------------------------------------------------------------------
@@ -826,6 +835,7 @@ solve_kernel(KernelParams P, const double* __restrict__ day_params, long long da
         }
         bool stack = !(hi == P.second_lo || hi == P.second_hi);  // :160
         unsigned dec = 0, zer = 0;
+        bool fragile = false;   // some running mass was zero up to rounding, but not exactly (see TRAJ_FRAGILE_BIT)
         if (kase != 4) {
 #ifdef CVAR_PROFILE_PHASES
             prof_probe = clock64() - prof_t1;
@@ -839,8 +849,10 @@ solve_kernel(KernelParams P, const double* __restrict__ day_params, long long da
                 const StripResult s = strip_memo<COPULA>(P, S, pt, L, parity, use_memo, k < MEMO_PER_ALPHA - 1, memo_visible, memo_n, a, b,
                                                          mid, cm, cl, ch, stack ? cl : cm, stack ? cm : ch, poison_mode);
                 ncell += s.cells;
+                const double r_prev = R;
                 R = (a == prev_upper) ? R + s.mass : R - s.mass;  // adjust_integral (:241-246)
                 if (R == 0.0) zer |= 1u << k;
+                else if (fabs(R) <= 1e-12 * fmax(fabs(r_prev), fabs(s.mass))) fragile = true;
                 stack = R < alpha;                                 // :298
                 if (stack) { dec |= 1u << k; lo = mid; u16* t = cl; cl = cm; cm = t; }
                 else       { hi = mid;       u16* t = ch; ch = cm; cm = t; }
@@ -852,7 +864,7 @@ solve_kernel(KernelParams P, const double* __restrict__ day_params, long long da
         }
         if (threadIdx.x == 0 && pt.rank == 0) {
             const long long o = (long long)ia * T + day;
-            traj[2 * o] = dec | ((unsigned)kase << 28);
+            traj[2 * o] = dec | ((unsigned)kase << 28) | (fragile ? TRAJ_FRAGILE_BIT : 0u);
             traj[2 * o + 1] = zer;
             if (mass_out) mass_out[o] = R;
             if (cells_out) cells_out[o] = ncell;
@@ -942,17 +954,21 @@ struct FinalizeParams {
 
 // one block per alpha: K = min( max_d need[case_d], first k at which every day's mass was exactly 0 )
 __global__ void finalize_reduce_kernel(FinalizeParams F, const unsigned* __restrict__ traj, long long T,
-                                       int* __restrict__ k_out) {
+                                       int* __restrict__ k_out, int* __restrict__ status_out) {
     __shared__ int s_need;
     __shared__ unsigned s_nonzero;
+    __shared__ int s_firm, s_fragile;   // days whose masses were never near 0 / days with a rounding-noise mass
     const int ia = blockIdx.x;
     if (threadIdx.x == 0) {
         s_need = 0;
         s_nonzero = 0;
+        s_firm = 0;
+        s_fragile = 0;
     }
     __syncthreads();
     int need = 0;
     unsigned nonzero = 0;
+    int firm = 0, fragile = 0;
     const unsigned mask = (F.max_iter >= 32) ? 0xffffffffu : ((1u << F.max_iter) - 1u);
     for (long long d = threadIdx.x; d < T; d += blockDim.x) {
         const unsigned w0 = traj[2 * (ia * T + d)], w1 = traj[2 * (ia * T + d) + 1];
@@ -960,19 +976,29 @@ __global__ void finalize_reduce_kernel(FinalizeParams F, const unsigned* __restr
         if (kase < 4) {
             need = max(need, F.need[kase]);
             nonzero |= (~w1) & mask;
+            if (w0 & TRAJ_FRAGILE_BIT) fragile = 1;
+            else if ((w1 & mask) == 0u) firm = 1;
         } else {
             nonzero |= mask;  // NaN mass is never == 0
+            firm = 1;
         }
     }
     atomicMax(&s_need, need);
     atomicOr(&s_nonzero, nonzero);
+    if (firm) atomicOr(&s_firm, 1);
+    if (fragile) atomicOr(&s_fragile, 1);
     __syncthreads();
     if (threadIdx.x == 0) {
-        int K = s_need;
+        int K = s_need, status = 0;
         const unsigned allzero = (~s_nonzero) & mask;
-        if (T > 0 && allzero) K = min(K, __ffs(allzero) - 1);
+        if (T > 0 && allzero && __ffs(allzero) - 1 < K) {
+            K = __ffs(allzero) - 1;
+            status |= STATUS_ZERO_EXIT_TAKEN;
+        }
+        if (T > 0 && s_fragile && !s_firm) status |= STATUS_ZERO_EXIT_AMBIGUOUS;
         if (F.forced[ia] >= 0) K = F.forced[ia];
         k_out[ia] = min(K, F.max_iter);
+        status_out[ia] = status;
     }
 }
 

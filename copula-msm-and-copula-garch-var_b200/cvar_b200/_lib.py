@@ -11,6 +11,7 @@ COPULA_ID = {"gaussian": 0, "student": 1, "plackett": 2}
 MARGINAL_ID = {"single": 0, "mixture": 1}
 COMPAT_SIGMA_SWAP, COMPAT_CASE_C_SIGN, COMPAT_NAN_TO_NUM, COMPAT_REFERENCE = 1, 2, 4, 7
 MAX_ALPHA = 8
+STATUS_ZERO_EXIT_TAKEN, STATUS_ZERO_EXIT_AMBIGUOUS = 1, 2
 CASE_NAMES = ("A", "B", "C", "D", "undefined")
 
 
@@ -57,6 +58,8 @@ _PROTOTYPES = {
     "cvar_strip_mass_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "cvar_solve_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "cvar_finalize_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "cvar_finalize_status_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
+    "cvar_finalize_status_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32]),
     "cvar_solve_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "cvar_test_special_host": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p]),
     "cvar_msm_forecast_host": (C.c_int, [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int64,

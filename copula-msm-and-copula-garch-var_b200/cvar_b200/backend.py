@@ -29,6 +29,7 @@ class SolveResult:
     cells: np.ndarray        # (n_alpha, T) grid cells evaluated per solve
     iterations: np.ndarray   # (n_alpha,) global bisection iteration count K
     kernel_ms: float         # device time of solve + finalize kernels
+    status: np.ndarray = None  # (n_alpha,) CVAR_STATUS_* bits of the finalize (zero-mass exit taken / ambiguous)
 
 
 def _ptr(a):
@@ -46,7 +47,7 @@ class VarPlan:
     """Run-constant state of the solve for one (copula, marginal family, grid, weights) combination."""
 
     def __init__(self, inputs: HotPathInputs, device: int | None = None, compat_flags: int = _lib.COMPAT_REFERENCE,
-                 max_iter: int = 0, first_guess: float = -3.0, second_guess=(-3.5, -2.0)):
+                 max_iter: int = 0, first_guess: float = -3.0, second_guess=(-3.5, -2.0), clip_lo: float = -5.0):
         lib = _lib.load()
         self._lib = lib
         d = _lib.CvarDesc()
@@ -61,6 +62,7 @@ class VarPlan:
         d.w0, d.w1 = float(inputs.weights[0]), float(inputs.weights[1])
         d.first_guess = float(first_guess)
         d.second_lo, d.second_hi = float(second_guess[0]), float(second_guess[1])
+        d.clip_lo = float(clip_lo)   # lower_bound of the reference's grid (calc_var_class.py:201)
         self.desc = d
         self.copula, self.marginal, self.n, self.q = inputs.copula, inputs.marginal, int(inputs.n), int(inputs.q)
         self._x = _f64(inputs.x, (self.n,))
@@ -152,7 +154,14 @@ class VarPlan:
         st = self._lib.cvar_solve_host(self._h, _ptr(day), T, _ptr(alphas), na, _ptr(forced), float(ptf_mean),
                                        _ptr(var), _ptr(case), _ptr(cells), _ptr(iters))
         _lib.check(st, "cvar_solve_host")
-        return SolveResult(var=var, case=case, cells=cells, iterations=iters, kernel_ms=float(self.info().last_kernel_ms))
+        return SolveResult(var=var, case=case, cells=cells, iterations=iters, kernel_ms=float(self.info().last_kernel_ms),
+                           status=self.last_status(na))
+
+    def last_status(self, n_alpha: int = 1) -> np.ndarray:
+        """CVAR_STATUS_* words of the plan's last finalize, one per alpha (cvar_finalize_status_host)."""
+        out = np.zeros(int(n_alpha), dtype=np.int32)
+        _lib.check(self._lib.cvar_finalize_status_host(self._h, _ptr(out), int(n_alpha)), "cvar_finalize_status_host")
+        return out
 
     def special(self, which: int, values) -> np.ndarray:
         """Device special functions (tests): see cvar_test_special_host."""

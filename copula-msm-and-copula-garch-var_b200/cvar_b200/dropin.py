@@ -11,6 +11,8 @@ the per-day solve should move to the GPU:
 
 `install` replaces `calc_var` and `compute_integral` (reference: utils/calc_var_class.py:95-212); nothing else
 of the reference is touched.  The GPU inputs are read from the same attributes the reference's methods read.
+`install_factory` adds the `backend=` keyword to the reference's `create_var_calculator` (utils/factory.py:9-31):
+"b200" or "reference" per calculator, CVAR_BACKEND as the process-wide default.
 """
 from __future__ import annotations
 
@@ -63,19 +65,39 @@ def _plan_for(v, inp: HotPathInputs, first_guess, second_guess) -> VarPlan:
     return cache[key]
 
 
+def backend_of(v) -> str:
+    """Backend of a driver object: the `.backend` its calculator got from the factory (install_factory), else the
+    environment variable CVAR_BACKEND, else "b200" (an installed drop-in defaults to the GPU)."""
+    import os
+
+    name = getattr(v.VaRCalculationMethod, "backend", None) or os.environ.get("CVAR_BACKEND") or "b200"
+    name = str(name).lower()
+    if name not in ("b200", "reference", "cpu"):
+        raise ValueError(f"Unsupported backend {name!r} (expected 'b200' or 'reference')")
+    return "reference" if name == "cpu" else name
+
+
 def calc_var(self, obj_var=0.05, first_guess=-3, second_guess=(-3.5, -2)):
+    if backend_of(self) == "reference":
+        return type(self)._cvar_b200_originals["calc_var"](self, obj_var, first_guess, second_guess)
     inp = inputs_from_reference_object(self)
     res = _plan_for(self, inp, first_guess, second_guess).solve(inp.day_params(), [obj_var], ptf_mean=self.ptf_mean)
     return res.var[0]
 
 
 def compute_integral(self, bounds):
+    if backend_of(self) == "reference":
+        return type(self)._cvar_b200_originals["compute_integral"](self, bounds)
     inp = inputs_from_reference_object(self)
     return _plan_for(self, inp, -3, (-3.5, -2)).strip_mass(inp.day_params(), np.asarray(bounds, float))
 
 
 def install(cls):
-    """Replace the hot-path methods of the reference's class; returns the originals for `uninstall`."""
+    """Replace the hot-path methods of the reference's class; returns the originals for `uninstall`.
+
+    Which path an object then takes is decided per object by `backend_of`: the factory keyword / CVAR_BACKEND."""
+    if "_cvar_b200_originals" in cls.__dict__:
+        return cls._cvar_b200_originals
     originals = {"calc_var": cls.calc_var, "compute_integral": cls.compute_integral}
     cls.calc_var = calc_var
     cls.compute_integral = compute_integral
@@ -84,5 +106,36 @@ def install(cls):
 
 
 def uninstall(cls):
-    for name, fn in getattr(cls, "_cvar_b200_originals", {}).items():
+    for name, fn in cls.__dict__.get("_cvar_b200_originals", {}).items():
         setattr(cls, name, fn)
+    if "_cvar_b200_originals" in cls.__dict__:
+        del cls._cvar_b200_originals
+
+
+def install_factory(factory_cls):
+    """Give the REFERENCE's factory the `backend=` keyword (utils/factory.py:9-31 takes two arguments):
+
+        ValueAtRiskCalculationFactory.create_var_calculator("student", "msm", backend="b200")
+
+    The calculator is the reference's own object; `.backend` ("b200" or "reference"; None = CVAR_BACKEND, default
+    "b200") tells the patched driver methods (install) which path to take."""
+    if "_cvar_b200_create" in factory_cls.__dict__:
+        return
+    original = factory_cls.create_var_calculator
+
+    def create_var_calculator(copula_type, estimation_type, backend=None):
+        calculator = original(copula_type, estimation_type)
+        if backend is not None:
+            if str(backend).lower() not in ("b200", "reference", "cpu"):
+                raise ValueError(f"Unsupported backend {backend!r} (expected 'b200' or 'reference')")
+            calculator.backend = str(backend).lower()
+        return calculator
+
+    factory_cls._cvar_b200_create = original
+    factory_cls.create_var_calculator = staticmethod(create_var_calculator)
+
+
+def uninstall_factory(factory_cls):
+    if "_cvar_b200_create" in factory_cls.__dict__:
+        factory_cls.create_var_calculator = staticmethod(factory_cls._cvar_b200_create)
+        del factory_cls._cvar_b200_create

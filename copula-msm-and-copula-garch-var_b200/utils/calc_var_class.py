@@ -53,7 +53,6 @@ class ValueAtRiskCalcualtion:
         self.VaRCalculationMethod = VaRCalculationMethod
         self.end_date = end_date
         self.weights = weights
-        self._plans = {}
 
         (self.in_sample_dict, self.rolling_windows_dict, self.mean_returns, self.end_date, self.out_sample_data,
          self.out_sample_N, self.dim, self.ptf_mean) = self.get_in_sample_data()
@@ -87,7 +86,6 @@ class ValueAtRiskCalcualtion:
         self.in_sample_params = self.marginals = self.densities = None
         self.out_sample_data = out_sample_data
         self.copula_params = copula_params
-        self._plans = {}
         m = VaRCalculationMethod
         if m.marginal_family == "single":
             if sigma is None:
@@ -191,13 +189,13 @@ class ValueAtRiskCalcualtion:
     def hot_path_inputs(self) -> HotPathInputs:
         return hot_path_inputs_from_attributes(self)
 
-    def _plan(self, first_guess=-3, second_guess=(-3.5, -2)) -> VarPlan:
-        key = (float(first_guess), float(second_guess[0]), float(second_guess[1]))
-        plan = self._plans.get(key)
-        if plan is None:
-            plan = VarPlan(self.hot_path_inputs(), first_guess=key[0], second_guess=key[1:])
-            self._plans[key] = plan
-        return plan
+    def _plan(self, first_guess=-3, second_guess=(-3.5, -2), inputs=None) -> VarPlan:
+        """Plan for the object's CURRENT run constants (copula parameters, weights, grid, vol levels, guesses): like
+        the reference, which re-reads its attributes on every calc_var, a refit or a changed `num_points` takes effect
+        on the next call; an unchanged object reuses its plan."""
+        from cvar_b200.dropin import _plan_for
+
+        return _plan_for(self, inputs if inputs is not None else self.hot_path_inputs(), first_guess, second_guess)
 
     # ---- the hot path ------------------------------------------------------------------------------
     def calc_var(self, obj_var=0.05, first_guess=-3, second_guess=(-3.5, -2)):
@@ -209,7 +207,7 @@ class ValueAtRiskCalcualtion:
         Each row equals what `calc_var(obj_var)` returns on its own."""
         start = time.time()
         inp = self.hot_path_inputs()
-        res = self._plan(first_guess, second_guess).solve(inp.day_params(), np.asarray(obj_vars, float),
+        res = self._plan(first_guess, second_guess, inp).solve(inp.day_params(), np.asarray(obj_vars, float),
                                                           ptf_mean=self.ptf_mean)
         self.last_solve = res
         self.last_calc_var_seconds = time.time() - start
@@ -218,7 +216,7 @@ class ValueAtRiskCalcualtion:
     def compute_integral(self, bounds):
         """Strip mass per day for `bounds[T, 2]` (the reference's grid build + joblib fan-out, :179-212)."""
         inp = self.hot_path_inputs()
-        return self._plan().strip_mass(inp.day_params(), np.asarray(bounds, float))
+        return self._plan(inputs=inp).strip_mass(inp.day_params(), np.asarray(bounds, float))
 
     @staticmethod
     def adjust_integral(new_result, prev_results, bounds, prev_upper):

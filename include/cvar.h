@@ -69,6 +69,8 @@ extern "C" {
 #define CVAR_ERR_NO_DEVICE (-6)     /* no usable CUDA device (there is no CPU fallback)  */
 #define CVAR_ERR_ABI (-7)           /* struct_size / abi_version mismatch                */
 #define CVAR_ERR_SMEM (-8)          /* grid too large for the shared memory of one SM    */
+#define CVAR_ERR_TABLE (-9)         /* Student-t: the per-plan quantile table is less accurate than 1e-11 for this nu
+                                       (checked against the iterative routine at plan creation); the plan is refused */
 
 #define CVAR_MAX_N 8192 /* hard cap; this version keeps a day's axis data in one SM's shared memory, which
                            limits n to ~4900 on B200 (cvar_plan_create returns CVAR_ERR_SMEM beyond) */
@@ -195,7 +197,8 @@ int cvar_strip_mass_device(cvar_plan_t* plan, const double* day_params, int64_t 
  * afterwards by cvar_finalize_*.
  *   traj  : [n_alpha][T][2] uint32
  *           word 0: bits 0..max_iter-1 = decision of iteration k (1: mass < alpha, lower end moves up),
- *                   bits 28..30 = bracket id CVAR_CASE_*
+ *                   bits 28..30 = bracket id CVAR_CASE_*, bit 31 = a running mass cancelled to rounding noise without
+ *                   being exactly 0 (feeds CVAR_STATUS_ZERO_EXIT_AMBIGUOUS below)
  *           word 1: bits 0..max_iter-1 = running mass after iteration k was exactly 0 (early-exit test,
  *                   calc_var_class.py:293-295)
  *   mass  : [n_alpha][T] running mass after the last recorded iteration, may be NULL
@@ -217,6 +220,24 @@ int cvar_solve_device(cvar_plan_t* plan, const double* day_params, int64_t T, co
 int cvar_finalize_device(cvar_plan_t* plan, const uint32_t* traj, int64_t T, int32_t n_alpha,
                          const int32_t* forced_iterations, double ptf_mean, double* var_out,
                          int32_t* case_out, int32_t* iterations_out, void* stream);
+
+/*
+ * Status words of the plan's LAST finalize (cvar_finalize_device, or the finalize inside cvar_solve_host), one per alpha:
+ *   CVAR_STATUS_ZERO_EXIT_TAKEN      the iteration count K was cut because the running mass of EVERY day of the batch was
+ *                                    exactly 0 after iteration K -- the reference's early exit (calc_var_class.py:293-295)
+ *   CVAR_STATUS_ZERO_EXIT_AMBIGUOUS  every day's running mass was 0 at some iteration either exactly or up to rounding (a
+ *                                    difference of two equal sums that cancelled to <= 1e-12 of its operands).  Whether the
+ *                                    reference takes its early exit on such a batch depends on the order in which its sums
+ *                                    happened to be formed; the VaR levels returned here follow the
+ *                                    no-exit branch, i.e. the bisection runs on to the quantile.  Only tiny batches whose
+ *                                    alpha lies below all the mass the grid holds under the first midpoint can get here.
+ * `_device`: status_out is a device array, the copy is enqueued on `stream` (after the finalize it reports on);
+ * `_host`: status_out is a host array, the call synchronises the plan's stream.
+ */
+#define CVAR_STATUS_ZERO_EXIT_TAKEN 1
+#define CVAR_STATUS_ZERO_EXIT_AMBIGUOUS 2
+int cvar_finalize_status_device(cvar_plan_t* plan, int32_t* status_out, int32_t n_alpha, void* stream);
+int cvar_finalize_status_host(cvar_plan_t* plan, int32_t* status_out, int32_t n_alpha);
 
 /*
  * One-call host entry point: H2D of day_params, solve, finalize, D2H of the VaR levels.

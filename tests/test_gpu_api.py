@@ -157,3 +157,51 @@ def test_error_paths(gpu):
     with pytest.raises(CvarError) as e:
         VarPlan(bad)
     assert e.value.status == -4
+
+
+@pytest.mark.parametrize("name", ["kat1_student_mixture", "kat2_gaussian_n100", "plackett_mr_w37_n80"])
+def test_calc_grids_and_integrals_results_seam(gpu, name):
+    """The lowest pure-function seam (reference: utils/calc_integral/calc_integral.py:8-119), called the way the
+    reference's compute_integral calls it (calc_var_class.py:194-212): np.unique'd bounds + inverse indices."""
+    from utils.calc_integral.calc_integral import calc_grids_and_integrals_results
+
+    v, inp, g = _driver_from_golden(name)
+    bounds = np.asarray(g["bounds"], float)
+    uniq, inverse = np.unique(bounds, axis=0, return_inverse=True)
+    got = calc_grids_and_integrals_results(
+        T=inp.T, unique_var_values=uniq, unique_indices=inverse, num_points=v.num_points, dim=v.dim, var_function=None,
+        lower_bound=-5, upper_bound=5, grids_generations_params=v.grids_generations_params,
+        integrations_params_t=v.integrations_params_t, integrations_params_static=v.integrations_params_static,
+        copula_params=v.copula_params, integrated_function=v.integrated_function, copula_density=v.copula_function,
+        unpack_copula_params=v.unpack_copula_params, weights=v.weights)
+    assert isinstance(got, np.ndarray) and got.shape == (inp.T,)
+    ref = np.asarray(g["ref_strip_mass"], float)
+    np.testing.assert_allclose(got, ref, rtol=2e-13, atol=1e-300)
+    np.testing.assert_array_equal(got, v.compute_integral(bounds))
+
+
+def test_quantile_table_budget_and_interleaved_plans(gpu, monkeypatch):
+    """(1) A Student-t plan whose quantile table misses its accuracy budget is refused (CVAR_ERR_TABLE), not used silently.
+    (2) Two live plans of the same kernel variant with different grids: the dynamic shared-memory opt-in belongs to the
+    kernel instantiation, not to a plan, so creating the small plan must not break later launches of the large one."""
+    from cvar_b200.backend import VarPlan
+    from cvar_b200._lib import CvarError
+    from cvar_b200 import synthetic as syn
+    from cvar_b200.inputs import make_inputs
+
+    small_in = make_inputs("student", "single", 100, rho=0.6, nu=5.3, sigma=syn.garch_sigma_path(4))
+    monkeypatch.setenv("CVAR_TQ_BUDGET", "1e-30")
+    with pytest.raises(CvarError) as e:
+        VarPlan(small_in)
+    assert e.value.status == -9
+    monkeypatch.delenv("CVAR_TQ_BUDGET")
+    big_in = make_inputs("student", "single", 2048, rho=0.6, nu=5.3, sigma=syn.garch_sigma_path(3))
+    with VarPlan(big_in) as big, VarPlan(big_in) as reference_plan:
+        expected = reference_plan.solve(big_in.day_params(), [0.01]).var
+        with VarPlan(small_in) as small:                          # same variant, ~20x less shared memory
+            assert small.info().kernel_variant == big.info().kernel_variant
+            assert small.info().tq_table_max_rel_err <= 1e-11
+            first = small.solve(small_in.day_params(), [0.01]).var
+            np.testing.assert_array_equal(big.solve(big_in.day_params(), [0.01]).var, expected)
+            np.testing.assert_array_equal(small.solve(small_in.day_params(), [0.01]).var, first)
+        np.testing.assert_array_equal(big.solve(big_in.day_params(), [0.01]).var, expected)

@@ -186,3 +186,86 @@ def test_window_slices_cover_the_series_and_match_the_day_shards():
                 assert r0 + (w - d0) * stride == w * stride and w * stride + N <= r1
             seen_days += list(range(d0, d1))
         assert seen_days == list(range(T))
+
+
+def test_factory_backend_selection(monkeypatch):
+    """`create_var_calculator(copula, estimation, backend=None)` + CVAR_BACKEND; this package holds the
+    B200 path only, so anything else raises instead of falling back to a CPU path (reference: utils/factory.py:9-31)."""
+    from utils.factory import ValueAtRiskCalculationFactory as F
+
+    monkeypatch.delenv("CVAR_BACKEND", raising=False)
+    assert F.create_var_calculator("student", "msm").backend == "b200"
+    assert F.create_var_calculator("student", "msm", backend="B200").backend == "b200"
+    assert F.create_var_calculator("plackett", "garch", "b200").backend == "b200"      # third positional argument
+    monkeypatch.setenv("CVAR_BACKEND", "b200")
+    assert F.create_var_calculator("gaussian", "garch").backend == "b200"
+    monkeypatch.setenv("CVAR_BACKEND", "reference")
+    with pytest.raises(ValueError, match="no CPU fallback"):
+        F.create_var_calculator("gaussian", "garch")
+    assert F.create_var_calculator("gaussian", "garch", backend="b200").backend == "b200"   # the argument wins
+    with pytest.raises(ValueError, match="Unsupported backend"):
+        F.create_var_calculator("gaussian", "garch", backend="cpu")
+    with pytest.raises(ValueError, match="Unsupported estimation type"):
+        F.create_var_calculator("clayton", "garch", backend="b200")
+
+
+def test_dropin_adds_the_backend_keyword_to_a_two_argument_factory(monkeypatch):
+    """`install_factory` on a factory with the reference's signature; the patched driver methods dispatch per object."""
+    import types
+    import cvar_b200.dropin as dropin
+
+    class Factory:                               # the reference's shape: a staticmethod of two arguments
+        @staticmethod
+        def create_var_calculator(copula_type, estimation_type):
+            return types.SimpleNamespace(copula_type=copula_type, estimation_type=estimation_type)
+
+    class Driver:
+        def calc_var(self, obj_var=0.05, first_guess=-3, second_guess=(-3.5, -2)):
+            return ("cpu path", obj_var)
+
+        def compute_integral(self, bounds):
+            return ("cpu path", bounds)
+
+    dropin.install_factory(Factory)
+    dropin.install_factory(Factory)              # idempotent
+    dropin.install(Driver)
+    try:
+        monkeypatch.delenv("CVAR_BACKEND", raising=False)
+        v = Driver()
+        v.VaRCalculationMethod = Factory.create_var_calculator("student", "garch", backend="reference")
+        assert dropin.backend_of(v) == "reference" and v.calc_var(obj_var=0.01) == ("cpu path", 0.01)
+        assert v.compute_integral("b") == ("cpu path", "b")
+        v.VaRCalculationMethod = Factory.create_var_calculator("student", "garch")
+        assert dropin.backend_of(v) == "b200"                      # installed drop-in: the GPU unless told otherwise
+        monkeypatch.setenv("CVAR_BACKEND", "cpu")
+        assert dropin.backend_of(v) == "reference" and v.calc_var() == ("cpu path", 0.05)
+        v.VaRCalculationMethod = Factory.create_var_calculator("student", "garch", backend="b200")
+        assert dropin.backend_of(v) == "b200"
+        with pytest.raises(ValueError, match="Unsupported backend"):
+            Factory.create_var_calculator("student", "garch", backend="tpu")
+    finally:
+        dropin.uninstall(Driver)
+        dropin.uninstall_factory(Factory)
+    assert Driver().calc_var() == ("cpu path", 0.05) and "_cvar_b200_create" not in Factory.__dict__
+    assert Factory.create_var_calculator("a", "b").copula_type == "a"
+
+
+def test_calc_integral_seam_recognises_the_copula_family():
+    """utils.calc_integral.calc_integral (reference: calc_integral.py:8-25): family from the hooks it is handed."""
+    from utils.calc_integral.calc_integral import calc_grids_and_integrals_results, copula_family_of
+    from utils.factory import ValueAtRiskCalculationFactory as F
+    import inspect
+
+    ref_args = ["T", "unique_var_values", "unique_indices", "num_points", "dim", "var_function", "lower_bound", "upper_bound",
+                "grids_generations_params", "integrations_params_t", "integrations_params_static", "copula_params",
+                "integrated_function", "copula_density", "unpack_copula_params", "weights"]
+    assert list(inspect.signature(calc_grids_and_integrals_results).parameters) == ref_args
+    for copula, params in (("student", np.array([5.3, 0.6])), ("gaussian", np.array([0.6])), ("plackett", 4.2)):
+        m = F.create_var_calculator(copula, "garch")
+        assert copula_family_of(m.copula_density, m.unpack_copula_params, params) == copula
+        # anonymous hooks: fall back to the shape of what unpack_copula_params returns
+        unpack = m.unpack_copula_params
+        assert copula_family_of(lambda *a, **k: None, lambda p: unpack(p), params) == copula
+    with pytest.raises(NotImplementedError):
+        calc_grids_and_integrals_results(1, np.zeros((1, 2)), np.zeros(1, int), 10, 3, None, -5, 5, None, None, None, None,
+                                         None, None, None, np.ones(3) / 3)
