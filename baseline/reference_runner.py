@@ -1,4 +1,4 @@
-"""Where the UNMODIFIED reference can be imported from (test and bench helper, never imported by the product).
+"""Running the UNMODIFIED reference (test and bench helper, never imported by the product).
 
 `baseline/_ref` is what `baseline/install_reference.sh` pip-installs from the read-only checkout (git-ignored, travels to
 the GPU box); in the build container the checkout itself, /root/reference, also works.  The reference's `utils` package
@@ -10,6 +10,10 @@ from __future__ import annotations
 import os
 import sys
 from pathlib import Path
+
+import json
+import subprocess
+import textwrap
 
 REPO = Path(__file__).resolve().parent.parent
 PKG_ROOT = REPO / "copula-msm-and-copula-garch-var_b200"
@@ -77,3 +81,39 @@ def build_reference_object(copula_type, estimation, n, copula_params, weights=(0
     v.integrated_function = m.integrated_function
     return v
 '''
+
+
+TIME_CALC_VAR = BUILD_OBJECT + textwrap.dedent("""
+    import contextlib, io, json, pickle, sys, time
+    case = pickle.load(open(sys.argv[1], "rb"))
+    v = build_reference_object(**case["object"])
+    times, var = [], None
+    for _ in range(case["repeats"]):
+        t0 = time.perf_counter()
+        with contextlib.redirect_stdout(io.StringIO()):          # the reference prints timings
+            var = np.asarray(v.calc_var(obj_var=case["alpha"]))
+        times.append(time.perf_counter() - t0)
+    pickle.dump({"seconds": times, "var": var}, open(sys.argv[2], "wb"))
+""")
+
+
+def time_reference_calc_var(inp, alpha: float, repeats: int = 2, timeout: float = 1800.0, workdir=None) -> dict:
+    """Run the unmodified reference's `calc_var(obj_var=alpha)` on the inputs of `inp` (cvar_b200.inputs.HotPathInputs)
+    `repeats` times in one subprocess (first call = numba compilation + joblib worker start, later calls warm).
+    Returns {"seconds": [...], "var": ndarray}.  Raises FileNotFoundError without a reference install."""
+    import pickle
+    import tempfile
+
+    estimation = "msm" if inp.marginal == "mixture" else "garch"
+    obj = dict(copula_type=inp.copula, estimation=estimation, n=int(inp.n), copula_params=inp.copula_params(),
+               weights=tuple(float(w) for w in inp.weights), ptf_mean=float(inp.ptf_mean), sigma=inp.sigma, probs=inp.probs,
+               sigma_states=inp.sigma_states)
+    with tempfile.TemporaryDirectory(dir=workdir) as tmp:
+        tmp = Path(tmp)
+        pickle.dump({"object": obj, "alpha": float(alpha), "repeats": int(repeats)}, open(tmp / "in.pkl", "wb"))
+        env = reference_env(tmp / "stubs", with_backend=False)
+        out = subprocess.run([sys.executable, "-c", TIME_CALC_VAR, str(tmp / "in.pkl"), str(tmp / "out.pkl")], env=env,
+                             cwd=tmp, capture_output=True, text=True, timeout=timeout)
+        if out.returncode != 0:
+            raise RuntimeError("reference run failed: " + out.stderr[-1500:])
+        return pickle.load(open(tmp / "out.pkl", "rb"))

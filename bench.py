@@ -6,11 +6,21 @@ workload is BASELINE.json configs[2] -- the configuration the metric is quoted o
 grid"): Student-t copula + MSM k=8 (q = 9 merged vol states) mixture marginals, 99 % VaR, 1000 days, n = 2048.
 Other configurations: --workload c1|c2|c3|c4|c5_<copula>_<single|mixture>.
 
-Prints ONE JSON line (rank 0).  `value` is whole-job throughput with the per-day parameters resident in HBM;
-`e2e` goes through the host-buffer C ABI (pinned host memory in, VaR vector out); `roofline` is the solve
-kernel against the FP64-pipe peak measured in the same run; `cpu_baseline` is the NumPy/SciPy oracle port timed
-on this box's host cores.  `--impl reference` times that CPU port alone (the reference itself is pure
-Python/numba and does not exist on the GPU box).
+Prints ONE JSON line (rank 0):
+  value         whole-job throughput, per-day parameters resident in HBM (weak scaling: `--days` per GPU; `--scaling
+                strong`: `--days-total` split over the GPUs); every step = solve kernel, all-gather of the decision words
+                (N > 1), finalize, timed per step with CUDA events, max over ranks
+  e2e           the same through the host-buffer API: pinned host parameters in, VaR vector out, copies inside the timing
+  roofline      the solve kernel against the FP64 pipe: algorithmic flops (SURVEY 8(d) convention) over the DFMA peak
+                measured in the same run, and `cell_pipe_frac`, the pipe share of the ISSUED FP64 instructions of the cells
+  strong        (default line) a second, shorter measurement with the total number of days fixed at 8000
+  phases_us     solve / all-gather / finalize of one step, timed one after the other
+  pipelined     throughput with a step's collective + finalize overlapped with the next step's solve (ShardedSolver)
+  cpu_baseline  the NumPy/SciPy oracle port on this box's host cores (N = 1), plus -- when a reference install is present
+                (baseline/_ref) -- the UNMODIFIED reference's calc_var timed on BASELINE configs[0]
+  parity        max |dVaR| against the oracle on a sample of days spread over all shards, exceedance counts
+`--impl reference` times the CPU path alone: the unmodified reference for c1 (when installed), else the oracle port
+(the reference's materialised grids cannot hold the n = 2048 mixture configurations).
 """
 from __future__ import annotations
 
@@ -26,21 +36,14 @@ from pathlib import Path
 import numpy as np
 
 REPO = Path(__file__).resolve().parent
-for _p in (str(REPO / "copula-msm-and-copula-garch-var_b200"), str(REPO)):
+for _p in (str(REPO / "copula-msm-and-copula-garch-var_b200"), str(REPO), str(REPO / "baseline")):
     if _p not in sys.path:
         sys.path.insert(0, _p)
 
 METRIC = "VaR solves/sec (day x alpha)"
 UNIT = "solves/s"
 DEFAULT_WORKLOAD = "c3"
-# dram__bytes_read.sum + dram__bytes_write.sum of one solve_kernel launch, from the committed ncu --set full captures
-# (profiles/r1_c3_solve_kernel_v12_ncu_summary.txt, profiles/r1_c4_solve_kernel_v12_ncu_summary.txt); the kernel
-# reads 144 KB (c3) / 16 KB (c4) of per-day parameters plus the plan tables (c3: 0.6 MB of mixture state tables, mostly
-# L2 hits) and writes 8-16 KB of decision words that stay in L2.
-NCU_DRAM_BYTES_PER_LAUNCH = {"c3": 889856, "c4": 140032}
-# sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active from the same captures: the ISSUED-instruction view of
-# the FP64 pipe, next to the algorithmic-flop fraction (which can exceed 1)
-NCU_FP64_PIPE_PCT = {"c3": 51.9, "c4": 50.0}
+STRONG_DAYS_TOTAL = 8000
 WORKLOAD_DESCRIPTIONS = {
     "c1": "BASELINE configs[0]: Gaussian copula + GARCH(1,1) sigma path, n=100, 99% VaR",
     "c2": "BASELINE configs[1]: Student-t copula + GARCH(1,1), n=1024, 95%/99% VaR",
@@ -85,6 +88,27 @@ def make_pool(workers):
     import multiprocessing as mp
     from concurrent.futures import ProcessPoolExecutor
     return ProcessPoolExecutor(max_workers=workers, mp_context=mp.get_context("spawn"))
+
+
+def reference_unmodified_c1(repeats=2):
+    """The UNMODIFIED reference's calc_var on BASELINE configs[0] (n=100, T=250), warm call; None without an install."""
+    try:
+        from reference_runner import reference_root, time_reference_calc_var
+    except ImportError:
+        return None, "baseline/reference_runner.py missing"
+    if reference_root() is None:
+        return None, "no reference install on this box (baseline/install_reference.sh was not run)"
+    from cvar_b200 import synthetic as syn
+    inp, alphas = syn.baseline_config("c1")
+    try:
+        r = time_reference_calc_var(inp, alphas[0], repeats=repeats)
+    except Exception as exc:  # noqa: BLE001  (reported in the record, the GPU numbers do not depend on it)
+        return None, f"reference run failed: {str(exc)[-300:]}"
+    warm = min(r["seconds"][1:]) if len(r["seconds"]) > 1 else r["seconds"][0]
+    return {"value": inp.T / warm, "unit": UNIT, "kind": "reference", "cores": len(os.sched_getaffinity(0)),
+            "workload": "c1 (Gaussian + GARCH, n=100, 250 days, alpha=1%)", "seconds_warm_call": warm,
+            "seconds_first_call": r["seconds"][0],
+            "path": "utils/calc_var_class.py:95-177 via numba + joblib(n_jobs=-1), unmodified, from baseline/_ref"}, r["var"]
 
 
 # ------------------------------------------------------------------------------------------------
@@ -142,33 +166,71 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------
-def build_workload(name, days_per_gpu, n, world, rank):
+def build_workload(name, days_total, n, world, rank):
     from cvar_b200 import synthetic as syn
     from cvar_b200.distributed import shard_bounds
-    defaults_T = {"c1": 250, "c2": 1000, "c3": 1000, "c4": 1000}
-    per = days_per_gpu or defaults_T.get(name, 1000)
-    inp_all, alphas = syn.baseline_config(name, T=per * world, n=n)
-    lo, hi = shard_bounds(per * world, world, rank)
-    return inp_all, inp_all.take_days(slice(lo, hi)), tuple(alphas), per
+    inp_all, alphas = syn.baseline_config(name, T=days_total, n=n)
+    lo, hi = shard_bounds(inp_all.T, world, rank)
+    return inp_all, inp_all.take_days(slice(lo, hi)), tuple(alphas)
 
 
-def workload_config(name, inp, alphas, per, world):
+def default_days(name):
+    return {"c1": 250, "c2": 1000, "c3": 1000, "c4": 1000}.get(name, 1000)
+
+
+def workload_config(name, inp, alphas, world, scaling):
+    per = -(-inp.T // world)
     return {
         "workload": WORKLOAD_DESCRIPTIONS.get(name, f"BASELINE configs[4] member {name}"), "name": name,
         "copula": inp.copula, "marginal": inp.marginal, "q": inp.q, "grid": f"{inp.n}x{inp.n}",
-        "days_per_gpu": per, "days_total": per * world, "alphas": list(alphas),
-        "solves_per_step": per * world * len(alphas), "sharding": f"days over {world} GPU(s), one all-gather of decision words",
+        "days_per_gpu": per, "days_total": inp.T, "alphas": list(alphas), "scaling": scaling,
+        "solves_per_step": inp.T * len(alphas), "sharding": f"days over {world} GPU(s), one all-gather of decision words",
         "l2": "256 MiB scratch write between timed steps (inputs are < 1 MiB and compute-bound)",
     }
 
 
+def traffic_record(name, info):
+    """DRAM bytes of one solve_kernel launch from the committed ncu capture of THIS kernel build, or None.
+
+    profiles/r2_traffic.json is written by tools/ncu_summary.py --traffic from `ncu --set full` reports and keyed by
+    workload; an entry is only used when the kernel variant and CTA shape it was captured with match the running plan."""
+    path = REPO / "profiles" / "r2_traffic.json"
+    if not path.exists():
+        return None
+    try:
+        entry = json.loads(path.read_text()).get(name)
+    except (OSError, ValueError):
+        return None
+    if not entry or entry.get("kernel_variant") != info.kernel_variant or entry.get("threads_per_cta") != info.threads_per_cta:
+        return None
+    return entry
+
+
 def run_reference(args, world, rank):
-    """--impl reference: the CPU port of the path on all host cores, bounded sample of the same workload."""
+    """--impl reference: the reference's CPU implementation of the path on all host cores.
+
+    c1 with a reference install: the UNMODIFIED reference (kind "reference"), one step = its calc_var over the 250 days.
+    Otherwise the oracle port (kind "port") on a bounded sample of the same workload."""
     if rank != 0:
         return
     name = args.workload
-    inp_all, _, alphas, per = build_workload(name, args.days, args.n, 1, 0)
+    days_total = args.days_total or (args.days or default_days(name))
+    inp_all, _, alphas = build_workload(name, days_total, args.n, 1, 0)
     workers = len(os.sched_getaffinity(0))
+    cfg = workload_config(name, inp_all, alphas, 1, "weak")
+    if name == "c1" and args.n is None and args.days is None and args.days_total is None:
+        ref, _ = reference_unmodified_c1(repeats=max(2, args.warmup + args.steps))
+        if ref is not None:
+            value = ref["value"]
+            print(json.dumps({
+                "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": 1e3 * ref["seconds_warm_call"], "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
+                "cpu_baseline": {"value": value, "unit": UNIT, "cores": workers, "kind": "reference",
+                                 "sample": "all 250 days x 1 alpha, warm call"},
+                "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0, "note": ref["path"]}))
+            return
     sample = list(range(0, inp_all.T, max(1, inp_all.T // args.cpu_sample_days)))[: args.cpu_sample_days]
     pool = make_pool(workers)
     try:
@@ -184,7 +246,6 @@ def run_reference(args, world, rank):
     nsolve = len(sample) * len(alphas)
     value = nsolve * args.steps / t
     sample_txt = f"{len(sample)} of {inp_all.T} days x {len(alphas)} alpha(s) per step, n={inp_all.n}"
-    cfg = workload_config(name, inp_all, alphas, per, 1)
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -192,26 +253,51 @@ def run_reference(args, world, rank):
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": workers, "kind": "port", "sample": sample_txt},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-        "note": "NumPy/SciPy restatement of the reference's strip scheme (oracle/var_oracle.py), one process per host "
-                "core; the reference itself (numba/joblib, materialised grids) is slower and cannot hold n=2048 mixtures",
+        "note": "kind=port: NumPy/SciPy restatement of the reference's strip scheme (oracle/var_oracle.py), one process per "
+                "host core -- a STAND-IN that is faster than the reference itself (numba/joblib, materialised grids), which "
+                "cannot hold n=2048 mixtures; the unmodified reference is timed on c1 (`--impl reference --workload c1`, "
+                "and `cpu_baseline.reference_unmodified` of the default line)",
     }))
+
+
+def timed_steps(step, steps, scratch, barrier, dev, world):
+    """K steps, each between a pair of CUDA events on the launching stream (L2 flushed before each, outside the pair);
+    returns the sum of the per-step device times in ms, max over ranks."""
+    import torch
+    import torch.distributed as dist
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    out = None
+    for a, b in ev:
+        scratch.zero_()
+        a.record()
+        out = step()
+        b.record()
+    barrier()
+    total_ms = sum(a.elapsed_time(b) for a, b in ev)
+    tt = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    return float(tt.item()), out
 
 
 def run_b200(args, world, rank, local_rank):
     import torch
     import torch.distributed as dist
     from cvar_b200.backend import VarPlan, fp64_peak_tflops
-    from cvar_b200.distributed import solve_sharded
-    from cvar_b200.workmodel import algorithmic_flops
+    from cvar_b200.distributed import ShardedSolver, solve_sharded
+    from cvar_b200.workmodel import algorithmic_flops, cell_fp64_pipe_fraction, issued_fp64_per_cell
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the VaR backend has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     name = args.workload
-    inp_all, inp, alphas, per = build_workload(name, args.days, args.n, world, rank)
+    strong = args.scaling == "strong"
+    days_total = (args.days_total or STRONG_DAYS_TOTAL) if strong else (args.days or default_days(name)) * world
+    inp_all, inp, alphas = build_workload(name, days_total, args.n, world, rank)
     T_total, na = inp_all.T, len(alphas)
     plan = VarPlan(inp, device=local_rank)
+    plan.reserve(max(inp.T, 1))
     info = plan.info()
 
     d_day = torch.from_numpy(inp.day_params()).to(dev)
@@ -230,20 +316,9 @@ def run_b200(args, world, rank, local_rank):
         var, case, iters = step()
     barrier()
     # ---- value: device-resident inputs, K steps, CUDA events, max over ranks -------------------------
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     t_region0 = time.perf_counter()
-    for a, b in ev:
-        scratch.zero_()                      # L2 flush, outside the per-step timing
-        a.record()
-        var, case, iters = step()
-        b.record()
-    barrier()
+    total_ms, (var, case, iters) = timed_steps(step, args.steps, scratch, barrier, dev, world)
     t_region1 = time.perf_counter()
-    total_ms = sum(a.elapsed_time(b) for a, b in ev)
-    tt = torch.tensor([total_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    total_ms = float(tt.item())
     value = T_total * na * args.steps / (total_ms * 1e-3)
 
     # ---- roofline: the solve kernel alone, on the launching stream ------------------------------------
@@ -263,6 +338,26 @@ def run_b200(args, world, rank, local_rank):
     flops_launch = algorithmic_flops(inp.copula, inp.marginal, inp.q, inp.n, cells_np)
     achieved_tf = flops_launch / (kernel_ms * 1e-3) / 1e12
     peak_tf, peak_ms = fp64_peak_tflops(local_rank, 100.0)
+    cell_frac = cell_fp64_pipe_fraction(info.kernel_variant, info.pow_octaves, cells_np, kernel_ms * 1e-3, peak_tf)
+
+    # ---- phases and the pipelined variant ---------------------------------------------------------------
+    solver = ShardedSolver(plan, T_total, na, inp.T)
+    phases = solver.phase_us(d_day, alphas, ptf_mean=inp.ptf_mean, repeats=5)
+    for _ in range(3):
+        solver.step(d_day, alphas, ptf_mean=inp.ptf_mean)
+    solver.synchronize()
+    barrier()
+    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    p0.record()
+    for _ in range(args.steps):
+        solver.step(d_day, alphas, ptf_mean=inp.ptf_mean)
+    solver.synchronize()
+    p1.record()
+    barrier()
+    tp = torch.tensor([p0.elapsed_time(p1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tp, op=dist.ReduceOp.MAX)
+    pipelined_value = T_total * na * args.steps / (float(tp.item()) * 1e-3)
 
     # ---- e2e: host buffers through the public API, H2D + kernels + D2H inside the timed region ---------
     pin_in = torch.from_numpy(np.ascontiguousarray(inp.day_params())).pin_memory()
@@ -271,7 +366,7 @@ def run_b200(args, world, rank, local_rank):
         day_np, out_np = pin_in.numpy(), pin_out.numpy()
 
         def e2e_step():
-            plan.solve(day_np, alphas, ptf_mean=inp.ptf_mean, out=out_np)
+            plan.solve(day_np, alphas, ptf_mean=inp.ptf_mean, out=out_np, details=False)
     else:
         d_in = torch.empty_like(d_day)
 
@@ -295,60 +390,116 @@ def run_b200(args, world, rank, local_rank):
     h2d = int(pin_in.numel() * 8) * world
     d2h = int(pin_out.numel() * 8) * (world if world > 1 else 1)
 
+    # ---- strong scaling at a fixed total (default line only): 8000 days split over the ranks ------------
+    strong_rec = None
+    if not strong and args.strong_steps > 0 and name in ("c2", "c3", "c4"):
+        s_all, s_inp, _ = build_workload(name, STRONG_DAYS_TOTAL, args.n, world, rank)
+        s_plan = VarPlan(s_inp, device=local_rank)
+        s_plan.reserve(max(s_inp.T, 1))
+        s_day = torch.from_numpy(s_inp.day_params()).to(dev)
+
+        def s_step():
+            return solve_sharded(s_plan, s_day, s_all.T, alphas, ptf_mean=s_inp.ptf_mean)
+        for _ in range(2):
+            s_step()
+        barrier()
+        s_ms, _ = timed_steps(s_step, args.strong_steps, scratch, barrier, dev, world)
+        strong_rec = {"days_total": s_all.T, "days_per_gpu": -(-s_all.T // world), "steps": args.strong_steps,
+                      "ms_per_step": s_ms / args.strong_steps, "value": s_all.T * na * args.strong_steps / (s_ms * 1e-3),
+                      "unit": UNIT, "note": "same workload with the total number of days fixed (strong scaling over --gpus)"}
+        s_plan.close()
+
     if sampler:
         sampler.stop()
+    var_np = var.cpu().numpy()
+    iters_np = [int(k) for k in iters.cpu().numpy()]
     if rank != 0:
         return
     clocks = sampler.summary(t_region0, t_region1)
-
+    traffic = traffic_record(name, info)
+    ordered = inp.T > 2 * info.sm_count * max(info.ctas_per_sm, 1)
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f64", "data": "synthetic", "config": workload_config(name, inp_all, alphas, per, world),
+        "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic", "config": workload_config(name, inp_all, alphas, world, args.scaling),
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "path": "cvar_solve_host (pinned host buffers)" if world == 1 else
-                        "pinned H2D + cvar_solve_device + NCCL all-gather + cvar_finalize_device + D2H"},
+                        "pinned H2D + cvar_solve_device + NCCL all-gather + cvar_finalize_blocked_device + D2H"},
         # kernels of this repo per timed step: [order_key_kernel when the batch exceeds two waves of CTAs,] solve_kernel,
         # finalize_reduce_kernel, finalize_apply_kernel (the radix sort of the launch order is cub's, not counted)
-        "gpu_launches": (4 if inp.T > 2 * info.sm_count * max(info.ctas_per_sm, 1) else 3) * args.steps,
+        "gpu_launches": (4 if ordered else 3) * args.steps,
         "roofline": {
             "bound": "fp64", "kernel": f"solve_kernel<{info.kernel_variant}> ({inp.copula})", "achieved": achieved_tf, "peak": peak_tf,
-            "unit": "TFLOP/s", "frac": achieved_tf / peak_tf, "traffic": NCU_DRAM_BYTES_PER_LAUNCH.get(name),
+            "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
+            "traffic": None if traffic is None else traffic["dram_bytes"],
+            "traffic_source": None if traffic is None else traffic.get("source"),
             "kernel_ms": kernel_ms, "algorithmic_flops_per_launch": flops_launch,
-            "ncu_fp64_pipe_pct_of_active_cycles": NCU_FP64_PIPE_PCT.get(name),
+            "cell_pipe_frac": cell_frac,
+            "issued_fp64_per_cell": issued_fp64_per_cell(info.kernel_variant, info.pow_octaves),
             "cells_per_solve_mean": float(cells_np.mean()),
+            "frac_note": "frac = algorithmic flops (SURVEY 8(d): 80 per Student cell, exp = 30, log = 42) / time / measured DFMA "
+                         "peak; it exceeds 1 because the kernel issues far fewer FP64 instructions per cell than that convention "
+                         "charges.  cell_pipe_frac = cells x ISSUED FP64 instructions per cell (SASS count, tests/test_abi.py) / "
+                         "pipe slots in kernel_ms: a lower bound of ncu's sm__pipe_fp64_cycles_active (profiles/), which also "
+                         "sees the axis stage, row set-up and masked lanes",
             "peak_source": f"measured in this run: dependency-free DFMA micro-benchmark, {peak_ms:.0f} ms "
                            "(MEASURED_PEAKS.json has no FP64 entry; nominal 148 SM x 64 lanes x 2 x 1.965 GHz = 37.2)",
         },
-        "iterations": [int(k) for k in iters.cpu().numpy()],
+        "phases_us": {k: round(v, 2) for k, v in phases.items()},
+        "pipelined": {"value": pipelined_value, "unit": UNIT,
+                      "note": "ShardedSolver: all-gather + finalize of step i on a side stream under the solve of step i+1; "
+                              "whole K-step region between two events, no L2 flush between steps"},
+        "iterations": iters_np,
         "plan": {"ctas_per_sm": info.ctas_per_sm, "threads_per_cta": info.threads_per_cta,
                  "smem_bytes_per_cta": info.smem_bytes_per_cta, "sm_count": info.sm_count,
-                 "kernel_variant": info.kernel_variant},
+                 "kernel_variant": info.kernel_variant, "pow_octaves": info.pow_octaves, "chunk_days": int(info.chunk_days)},
     }
+    if strong_rec:
+        out["strong"] = strong_rec
 
-    # ---- cpu_baseline + parity on a bounded sample (rank 0, N = 1 only) ---------------------------------
-    if world == 1 and args.cpu_sample_days > 0:
+    # ---- cpu_baseline (N = 1) + parity on a bounded sample spread over ALL shards (rank 0, any N) --------
+    if args.cpu_sample_days > 0:
         from cvar_b200.backtest import exceedances      # the oracle itself is only executed inside the worker processes
         workers = len(os.sched_getaffinity(0))
-        sample = list(range(0, inp.T, max(1, inp.T // args.cpu_sample_days)))[: args.cpu_sample_days]
-        forced = [int(k) for k in iters.cpu().numpy()]
+        ndays = args.cpu_sample_days if world == 1 else min(args.cpu_sample_days, 64)
+        sample = list(range(0, T_total, max(1, T_total // ndays)))[:ndays]
         pool = make_pool(workers)
         try:
-            cpu_port_solve(inp, alphas[:1], sample[:workers], forced[:1], pool, workers)    # spin the workers up
-            dt, cpu_var = cpu_port_solve(inp, alphas, sample, forced, pool, workers)
+            cpu_port_solve(inp_all, alphas[:1], sample[:workers], iters_np[:1], pool, workers)    # spin the workers up
+            dt, cpu_var = cpu_port_solve(inp_all, alphas, sample, iters_np, pool, workers)
         finally:
             pool.shutdown()
-        gpu_var = var.cpu().numpy()
+        gpu_var = var_np if world > 1 else var_np            # (n_alpha, T_total) on every rank
         max_dvar = max(float(np.max(np.abs(gpu_var[k][sample] - cpu_var[a]))) for k, a in enumerate(alphas))
         rng = np.random.default_rng(11)
         r_ptf = rng.standard_normal(len(sample)) * 1.2
         exc_equal = all(exceedances(gpu_var[k][sample], r_ptf) == exceedances(cpu_var[a], r_ptf)
                         for k, a in enumerate(alphas))
-        out["cpu_baseline"] = {"value": len(sample) * na / dt, "unit": UNIT, "cores": workers, "kind": "port",
-                               "sample": f"{len(sample)} of {inp.T} days x {na} alpha(s), n={inp.n}, {dt:.1f} s wall"}
         out["parity"] = {"max_abs_dvar_vs_oracle": max_dvar, "exceedance_counts_equal": bool(exc_equal),
-                         "days_checked": len(sample)}
+                         "days_checked": len(sample), "shards_covered": world, "iterations": iters_np,
+                         "note": "oracle re-solves the sampled days with the batch-wide iteration count the GPUs derived (Q7)"}
+        if world == 1:
+            out["cpu_baseline"] = {"value": len(sample) * na / dt, "unit": UNIT, "cores": workers, "kind": "port",
+                                   "sample": f"{len(sample)} of {inp.T} days x {na} alpha(s), n={inp.n}, {dt:.1f} s wall"}
+            if args.reference_unmodified:
+                ref, ref_var = reference_unmodified_c1()
+                if ref is None:
+                    out["cpu_baseline"]["reference_unmodified"] = {"unavailable": ref_var}
+                else:
+                    # the same c1 batch on the GPU, for the parity of the two and the ratio at the reference's own size
+                    from cvar_b200 import synthetic as syn
+                    c1, c1_alphas = syn.baseline_config("c1")
+                    with VarPlan(c1, device=local_rank) as c1_plan:
+                        for _ in range(3):
+                            c1_res = c1_plan.solve(c1.day_params(), c1_alphas, ptf_mean=c1.ptf_mean, details=False)
+                        t0 = time.perf_counter()
+                        for _ in range(20):
+                            c1_plan.solve(c1.day_params(), c1_alphas, ptf_mean=c1.ptf_mean, details=False)
+                        c1_s = (time.perf_counter() - t0) / 20
+                    ref["b200_e2e_same_workload"] = {"value": c1.T / c1_s, "unit": UNIT}
+                    ref["max_abs_dvar_b200_vs_reference"] = float(np.max(np.abs(c1_res.var[0] - ref_var)))
+                    out["cpu_baseline"]["reference_unmodified"] = ref
     print(json.dumps(out))
 
 
@@ -359,10 +510,16 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD)
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: --days per GPU (default); strong: --days-total split over the GPUs")
     ap.add_argument("--days", type=int, default=None, help="days per GPU (default: the configuration's own T)")
+    ap.add_argument("--days-total", type=int, default=None, help=f"total days with --scaling strong (default {STRONG_DAYS_TOTAL})")
     ap.add_argument("--n", type=int, default=None, help="grid points per axis (default: the configuration's own n)")
     ap.add_argument("--cpu-sample-days", type=int, default=128,
-                    help="days of the workload the CPU port solves (cpu_baseline leg / one --impl reference step)")
+                    help="days of the workload the CPU port solves (cpu_baseline / parity legs, one --impl reference step)")
+    ap.add_argument("--strong-steps", type=int, default=5, help="steps of the fixed-total measurement in the default line (0: off)")
+    ap.add_argument("--no-reference-unmodified", dest="reference_unmodified", action="store_false",
+                    help="skip timing the unmodified reference on c1 (N = 1, needs baseline/_ref)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 

@@ -355,16 +355,17 @@ int launch_strip(cvar_plan* p, const double* d_day, int64_t T, const double* d_b
     return (int)cudaGetLastError();
 }
 
-int launch_finalize(cvar_plan* p, const uint32_t* d_traj, int64_t T, int32_t n_alpha, const int32_t* forced,
+int launch_finalize(cvar_plan* p, const uint32_t* d_traj, int64_t T, int64_t block, int32_t n_alpha, const int32_t* forced,
                     double ptf_mean, double* d_var, int32_t* d_case, cudaStream_t st) {
     FinalizeParams F = p->fp;
     F.ptf_mean = ptf_mean;
     for (int i = 0; i < CVAR_MAX_ALPHA; ++i) F.forced[i] = (forced && i < n_alpha) ? forced[i] : -1;
-    finalize_reduce_kernel<<<n_alpha, 1024, 0, st>>>(F, d_traj, (long long)T, p->d_k, p->d_k + CVAR_MAX_ALPHA);
+    const long long blk = std::max<int64_t>(block, 1);
+    finalize_reduce_kernel<<<n_alpha, 1024, 0, st>>>(F, d_traj, (long long)T, blk, n_alpha, p->d_k, p->d_k + CVAR_MAX_ALPHA);
     CU_TRY(cudaGetLastError());
     const long long total = (long long)T * n_alpha;
     if (total > 0) {
-        finalize_apply_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(F, d_traj, (long long)T, n_alpha, p->d_k,
+        finalize_apply_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(F, d_traj, (long long)T, blk, n_alpha, p->d_k,
                                                                               d_var, d_case);
         CU_TRY(cudaGetLastError());
     }
@@ -854,14 +855,20 @@ int cvar_solve_device(cvar_plan_t* p, const double* day_params, int64_t T, const
 
 int cvar_finalize_device(cvar_plan_t* p, const uint32_t* traj, int64_t T, int32_t n_alpha, const int32_t* forced,
                          double ptf_mean, double* var_out, int32_t* case_out, int32_t* iterations_out, void* stream) {
+    return cvar_finalize_blocked_device(p, traj, T, T, n_alpha, forced, ptf_mean, var_out, case_out, iterations_out, stream);
+}
+
+int cvar_finalize_blocked_device(cvar_plan_t* p, const uint32_t* traj, int64_t T, int64_t block_days, int32_t n_alpha,
+                                 const int32_t* forced, double ptf_mean, double* var_out, int32_t* case_out,
+                                 int32_t* iterations_out, void* stream) {
     if (!p || (T > 0 && (!traj || !var_out))) return CVAR_ERR_NULL;
-    if (T < 0 || n_alpha < 1 || n_alpha > CVAR_MAX_ALPHA) return CVAR_ERR_SIZE;
+    if (T < 0 || n_alpha < 1 || n_alpha > CVAR_MAX_ALPHA || (T > 0 && block_days < 1)) return CVAR_ERR_SIZE;
     if (forced)
         for (int i = 0; i < n_alpha; ++i)
             if (forced[i] > p->kp.max_iter) return CVAR_ERR_PARAM;
     DeviceGuard guard(p->device);
     cudaStream_t st = (cudaStream_t)stream;
-    int rc = launch_finalize(p, traj, T, n_alpha, forced, ptf_mean, var_out, case_out, st);
+    int rc = launch_finalize(p, traj, T, block_days, n_alpha, forced, ptf_mean, var_out, case_out, st);
     if (rc) return rc;
     if (iterations_out)
         CU_TRY(cudaMemcpyAsync(iterations_out, p->d_k, sizeof(int) * n_alpha, cudaMemcpyDeviceToDevice, st));
@@ -916,7 +923,7 @@ int cvar_solve_host(cvar_plan_t* p, const double* day_params, int64_t T, const d
     CU_TRY(cudaEventRecord(p->ev0, p->stream));
     rc = launch_solve(p, d_day, T, A, d_trj, nullptr, cells_out ? d_cel : nullptr, p->stream);
     if (rc) return rc;
-    rc = launch_finalize(p, d_trj, T, n_alpha, forced, ptf_mean, d_var, case_out ? d_cas : nullptr, p->stream);
+    rc = launch_finalize(p, d_trj, T, T, n_alpha, forced, ptf_mean, d_var, case_out ? d_cas : nullptr, p->stream);
     if (rc) return rc;
     CU_TRY(cudaEventRecord(p->ev1, p->stream));
     if (T > 0) {

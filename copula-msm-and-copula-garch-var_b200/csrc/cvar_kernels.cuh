@@ -953,8 +953,15 @@ struct FinalizeParams {
 };
 
 // one block per alpha: K = min( max_d need[case_d], first k at which every day's mass was exactly 0 )
-__global__ void finalize_reduce_kernel(FinalizeParams F, const unsigned* __restrict__ traj, long long T,
-                                       int* __restrict__ k_out, int* __restrict__ status_out) {
+// The trajectory words may arrive in BLOCKS of `block` days -- [n_blocks][n_alpha][block][2], the layout an all-gather of
+// the per-rank [n_alpha][block][2] arrays produces -- so that no kernel has to reshuffle them; block == T is the plain
+// [n_alpha][T][2] layout.
+__device__ __forceinline__ long long traj_index(long long block, int n_alpha, int ia, long long d) {
+    return ((d / block) * n_alpha + ia) * block + d % block;
+}
+
+__global__ void finalize_reduce_kernel(FinalizeParams F, const unsigned* __restrict__ traj, long long T, long long block,
+                                       int n_alpha, int* __restrict__ k_out, int* __restrict__ status_out) {
     __shared__ int s_need;
     __shared__ unsigned s_nonzero;
     __shared__ int s_firm, s_fragile;   // days whose masses were never near 0 / days with a rounding-noise mass
@@ -971,7 +978,8 @@ __global__ void finalize_reduce_kernel(FinalizeParams F, const unsigned* __restr
     int firm = 0, fragile = 0;
     const unsigned mask = (F.max_iter >= 32) ? 0xffffffffu : ((1u << F.max_iter) - 1u);
     for (long long d = threadIdx.x; d < T; d += blockDim.x) {
-        const unsigned w0 = traj[2 * (ia * T + d)], w1 = traj[2 * (ia * T + d) + 1];
+        const long long o = traj_index(block, n_alpha, ia, d);
+        const unsigned w0 = traj[2 * o], w1 = traj[2 * o + 1];
         const unsigned kase = (w0 >> 28) & 7u;
         if (kase < 4) {
             need = max(need, F.need[kase]);
@@ -1002,13 +1010,13 @@ __global__ void finalize_reduce_kernel(FinalizeParams F, const unsigned* __restr
     }
 }
 
-__global__ void finalize_apply_kernel(FinalizeParams F, const unsigned* __restrict__ traj, long long T, int n_alpha,
-                                      const int* __restrict__ k_in, double* __restrict__ var_out,
+__global__ void finalize_apply_kernel(FinalizeParams F, const unsigned* __restrict__ traj, long long T, long long block,
+                                      int n_alpha, const int* __restrict__ k_in, double* __restrict__ var_out,
                                       int* __restrict__ case_out) {
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= T * n_alpha) return;
     const int ia = (int)(idx / T);
-    const unsigned w0 = traj[2 * idx];
+    const unsigned w0 = traj[2 * traj_index(block, n_alpha, ia, idx - (long long)ia * T)];
     const unsigned kase = (w0 >> 28) & 7u;
     double v = NAN;
     if (kase < 4) {

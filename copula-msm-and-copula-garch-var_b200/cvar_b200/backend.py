@@ -208,12 +208,24 @@ class VarPlan:
         _lib.check(st, "cvar_solve_device")
         return traj
 
-    def finalize_device(self, traj, ptf_mean: float = 0.0, forced_iterations=None, var=None, case=None, iterations=None):
-        """Enqueue the finalize kernels over a (possibly gathered) trajectory tensor (n_alpha, T, 2)."""
+    def finalize_device(self, traj, ptf_mean: float = 0.0, forced_iterations=None, var=None, case=None, iterations=None,
+                        T: int | None = None):
+        """Enqueue the finalize kernels over a (possibly gathered) trajectory tensor.
+
+        traj: (n_alpha, T, 2), or -- straight out of an all-gather, no reshuffling -- the blocked layout
+        (n_blocks, n_alpha, block_days, 2) with day d in block d // block_days; pass the true number of days `T` when
+        the last block is ragged (cvar_finalize_blocked_device)."""
         import torch
 
         self._check_tensor(traj, torch.int32, "traj")
-        na, T = traj.shape[0], traj.shape[1]
+        if traj.dim() == 4:
+            nb, na, block = traj.shape[0], traj.shape[1], traj.shape[2]
+            T = nb * block if T is None else int(T)
+            if not (nb - 1) * block < T <= nb * block and not (T == 0 and nb * block == 0):
+                raise ValueError(f"T = {T} does not fit {nb} blocks of {block} days")
+        else:
+            na, block = traj.shape[0], max(traj.shape[1], 1)
+            T = traj.shape[1]
         if var is None:
             var = torch.empty((na, T), dtype=torch.float64, device=traj.device)
         if case is None:
@@ -223,10 +235,10 @@ class VarPlan:
         forced = None if forced_iterations is None else np.ascontiguousarray(
             np.broadcast_to(np.asarray(forced_iterations, dtype=np.int32), (na,)))
         stream = torch.cuda.current_stream(traj.device).cuda_stream
-        st = self._lib.cvar_finalize_device(self._h, C.c_void_p(traj.data_ptr()), T, na, _ptr(forced), float(ptf_mean),
-                                            C.c_void_p(var.data_ptr()), C.c_void_p(case.data_ptr()),
-                                            C.c_void_p(iterations.data_ptr()), C.c_void_p(stream))
-        _lib.check(st, "cvar_finalize_device")
+        st = self._lib.cvar_finalize_blocked_device(self._h, C.c_void_p(traj.data_ptr()), T, block, na, _ptr(forced),
+                                                    float(ptf_mean), C.c_void_p(var.data_ptr()), C.c_void_p(case.data_ptr()),
+                                                    C.c_void_p(iterations.data_ptr()), C.c_void_p(stream))
+        _lib.check(st, "cvar_finalize_blocked_device")
         return var, case, iterations
 
     def strip_mass_device(self, day_params, bounds, out=None):

@@ -44,15 +44,122 @@ def gather_trajectories(traj_local: torch.Tensor, T_total: int, group=None) -> t
     return out[:, :T_total, :].contiguous()
 
 
+def gather_blocks(traj_local: torch.Tensor, T_total: int, group=None, out: torch.Tensor | None = None) -> torch.Tensor:
+    """All-gather the (n_alpha, T_local, 2) blocks into (world, n_alpha, per, 2), per = ceil(T_total / world): the
+    collective's own output layout, which `cvar_finalize_blocked_device` reads as it is -- no concatenate / permute /
+    copy kernel on either side of the collective.  Only a ragged last block is padded (one small copy on that rank)."""
+    world = dist.get_world_size(group)
+    na, t_local, two = traj_local.shape
+    per = -(-T_total // world)
+    if t_local > per:
+        raise ValueError(f"local block of {t_local} days exceeds ceil(T/world) = {per}")
+    if t_local < per:
+        padded = torch.zeros((na, per, two), dtype=traj_local.dtype, device=traj_local.device)
+        padded[:, :t_local] = traj_local
+        traj_local = padded
+    if out is None:
+        out = torch.empty((world, na, per, two), dtype=traj_local.dtype, device=traj_local.device)
+    dist.all_gather_into_tensor(out.view(-1), traj_local.contiguous().view(-1), group=group)
+    return out
+
+
 def solve_sharded(plan, day_params_local: torch.Tensor, T_total: int, alphas, ptf_mean: float = 0.0, group=None):
     """Solve this rank's days, gather the decision words, finalize the whole batch on every rank.
 
     Returns (var[n_alpha, T_total], case[n_alpha, T_total], iterations[n_alpha]) as CUDA tensors.
     """
     traj_local = plan.solve_device(day_params_local, alphas)
-    traj = gather_trajectories(traj_local, T_total, group) if dist.is_initialized() and dist.get_world_size(group) > 1 \
-        else traj_local
-    return plan.finalize_device(traj, ptf_mean=ptf_mean)
+    if not (dist.is_initialized() and dist.get_world_size(group) > 1):
+        return plan.finalize_device(traj_local, ptf_mean=ptf_mean)
+    return plan.finalize_device(gather_blocks(traj_local, T_total, group), ptf_mean=ptf_mean, T=T_total)
+
+
+class ShardedSolver:
+    """Repeated sharded solves of batches of one shape, with the collective off the critical path.
+
+    A step's all-gather + finalize (latency-bound: ~20-30 us on 8 GPUs against a ~2 ms solve) runs on a side stream while
+    the NEXT step's solve kernel already runs on the caller's stream; two sets of buffers alternate.  Results of `step`
+    are valid on the side stream: call `synchronize()` (the caller's stream waits for it) before reading them.
+    `phase_us()` times the three phases of one step separately (CUDA events, no overlap) for the benchmark record.
+    """
+
+    def __init__(self, plan, T_total: int, n_alpha: int, t_local: int, group=None):
+        self.plan, self.T, self.na, self.group = plan, int(T_total), int(n_alpha), group
+        self.sharded = dist.is_initialized() and dist.get_world_size(group) > 1
+        self.world = dist.get_world_size(group) if self.sharded else 1
+        self.per = -(-self.T // self.world)
+        dev = torch.device("cuda", plan.device)
+        self.side = torch.cuda.Stream(device=dev)
+        mk = lambda *shape, dtype: torch.empty(shape, dtype=dtype, device=dev)     # noqa: E731
+        self.buffers = []
+        for _ in range(2):
+            local = torch.zeros((self.na, self.per if self.sharded else t_local, 2), dtype=torch.int32, device=dev)
+            self.buffers.append(dict(
+                local=local, view=local[:, :t_local] if t_local < local.shape[1] else local,
+                blocks=mk(self.world, self.na, self.per, 2, dtype=torch.int32) if self.sharded else None,
+                var=mk(self.na, self.T, dtype=torch.float64), case=mk(self.na, self.T, dtype=torch.int32),
+                iters=mk(self.na, dtype=torch.int32), free=None))
+        self.t_local, self.flip = int(t_local), 0
+        plan.reserve(max(self.t_local, 1))
+
+    def _solve(self, buf, day_local, alphas):
+        # a ragged last block solves into a (n_alpha, t_local, 2) scratch and is copied into the padded block
+        if buf["view"] is buf["local"]:
+            self.plan.solve_device(day_local, alphas, traj=buf["local"])
+        else:
+            buf["local"][:, : self.t_local] = self.plan.solve_device(day_local, alphas)
+
+    def _finish(self, buf, ptf_mean):
+        if self.sharded:
+            dist.all_gather_into_tensor(buf["blocks"].view(-1), buf["local"].view(-1), group=self.group)
+            self.plan.finalize_device(buf["blocks"], ptf_mean=ptf_mean, var=buf["var"], case=buf["case"],
+                                      iterations=buf["iters"], T=self.T)
+        else:
+            self.plan.finalize_device(buf["local"], ptf_mean=ptf_mean, var=buf["var"], case=buf["case"], iterations=buf["iters"])
+
+    def step(self, day_local: torch.Tensor, alphas, ptf_mean: float = 0.0):
+        buf = self.buffers[self.flip]
+        self.flip ^= 1
+        main = torch.cuda.current_stream(self.side.device)
+        if buf["free"] is not None:
+            main.wait_event(buf["free"])          # the side stream is done with this buffer set (two steps ago)
+        self._solve(buf, day_local, alphas)
+        solved = torch.cuda.Event()
+        solved.record(main)
+        with torch.cuda.stream(self.side):
+            self.side.wait_event(solved)
+            self._finish(buf, ptf_mean)
+            buf["free"] = torch.cuda.Event()
+            buf["free"].record(self.side)
+        return buf["var"], buf["case"], buf["iters"]
+
+    def synchronize(self):
+        torch.cuda.current_stream(self.side.device).wait_stream(self.side)
+
+    def phase_us(self, day_local: torch.Tensor, alphas, ptf_mean: float = 0.0, repeats: int = 5) -> dict:
+        """{'solve': us, 'gather': us, 'finalize': us}: one step's phases one after the other on the current stream."""
+        buf = self.buffers[0]
+        self.synchronize()
+        torch.cuda.synchronize()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        acc = [0.0, 0.0, 0.0]
+        for _ in range(repeats):
+            if self.sharded:
+                dist.barrier(group=self.group)
+            ev[0].record()
+            self._solve(buf, day_local, alphas)
+            ev[1].record()
+            if self.sharded:
+                dist.all_gather_into_tensor(buf["blocks"].view(-1), buf["local"].view(-1), group=self.group)
+            ev[2].record()
+            src = buf["blocks"] if self.sharded else buf["local"]
+            self.plan.finalize_device(src, ptf_mean=ptf_mean, var=buf["var"], case=buf["case"], iterations=buf["iters"],
+                                      T=self.T if self.sharded else None)
+            ev[3].record()
+            torch.cuda.synchronize()
+            for k in range(3):
+                acc[k] += ev[k].elapsed_time(ev[k + 1]) * 1e3 / repeats
+        return {"solve": acc[0], "gather": acc[1], "finalize": acc[2]}
 
 
 def window_slice(T: int, N: int, world_size: int, rank: int, window_stride: int = 1) -> tuple[int, int, int, int]:

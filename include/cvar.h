@@ -220,6 +220,16 @@ int cvar_solve_device(cvar_plan_t* plan, const double* day_params, int64_t T, co
 int cvar_finalize_device(cvar_plan_t* plan, const uint32_t* traj, int64_t T, int32_t n_alpha,
                          const int32_t* forced_iterations, double ptf_mean, double* var_out,
                          int32_t* case_out, int32_t* iterations_out, void* stream);
+/*
+ * The same over trajectory words that arrive in blocks of `block_days` days, [n_blocks][n_alpha][block_days][2] with day d
+ * in block d / block_days: exactly what an all-gather of the ranks' [n_alpha][block_days][2] arrays leaves behind when
+ * every rank solves a contiguous block of ceil(T / ranks) days (the last block may be ragged: only its first
+ * T - (n_blocks - 1) * block_days days are read).  No reshuffling kernel between the collective and the finalize.
+ * block_days >= T is the plain layout of cvar_finalize_device.
+ */
+int cvar_finalize_blocked_device(cvar_plan_t* plan, const uint32_t* traj, int64_t T, int64_t block_days, int32_t n_alpha,
+                                 const int32_t* forced_iterations, double ptf_mean, double* var_out,
+                                 int32_t* case_out, int32_t* iterations_out, void* stream);
 
 /*
  * Status words of the plan's LAST finalize (cvar_finalize_device, or the finalize inside cvar_solve_host), one per alpha:

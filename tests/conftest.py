@@ -7,7 +7,7 @@ import pytest
 
 REPO = Path(__file__).resolve().parent.parent
 PKG_ROOT = REPO / "copula-msm-and-copula-garch-var_b200"
-for p in (str(PKG_ROOT), str(REPO)):
+for p in (str(PKG_ROOT), str(REPO), str(REPO / "baseline")):
     if p not in sys.path:
         sys.path.insert(0, p)
 
@@ -19,7 +19,11 @@ def pytest_configure(config):
     # the CUDA library is a build artefact (git-ignored): compile it if this checkout does not have it yet
     from cvar_b200.build import LIB_PATH, build_library
     if not LIB_PATH.exists():
-        build_library()
+        try:
+            build_library()
+        except Exception as exc:      # no nvcc on this checkout: the pure-CPU tests (oracle, goldens, gloo) still run;
+            import warnings           # ABI and gpu-marked tests fail or skip on their own when they load the library
+            warnings.warn(f"libcvar_b200.so is missing and could not be built: {exc}")
 
 
 NON_SOLVE_GOLDENS = {"forecast_producers"}

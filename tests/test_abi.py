@@ -99,3 +99,24 @@ def test_product_package_never_imports_the_oracle():
     offenders = [str(p) for p in pkg.rglob("*.py") if re.search(r"^\s*(from|import)\s+oracle\b", p.read_text(), flags=re.M)]
     offenders += [str(p) for p in pkg.rglob("*.cu*") if "oracle" in p.read_text()]
     assert not offenders
+
+
+def test_issued_fp64_per_cell_constants_match_the_sass():
+    """bench.py's `roofline.cell_pipe_frac` multiplies the cell counter by workmodel.FP64_PER_CELL: re-count those
+    constants in the SASS of the built library (tools/sass_loops.py lists every loop of a kernel with its FP64 count)."""
+    import shutil
+    import subprocess
+    import sys
+    from cvar_b200.build import LIB_PATH
+    from cvar_b200.workmodel import CELLS_IN_FLIGHT, FP64_PER_CELL
+
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not Path(cuobjdump).exists():
+        pytest.skip("cuobjdump not available")
+    sass = subprocess.run([cuobjdump, "-sass", str(LIB_PATH)], capture_output=True, text=True, check=True).stdout
+    for kv, (fast, slow) in FP64_PER_CELL.items():
+        loops = subprocess.run([sys.executable, str(REPO / "tools" / "sass_loops.py"), f"solve_kernelILi{kv}ELb0", "1000"],
+                               input=sass, capture_output=True, text=True, check=True).stdout
+        fp64_counts = {int(m.group(1)) for m in re.finditer(r"FP64\s+(\d+),", loops)}
+        for per_cell in {fast, slow}:
+            assert per_cell * CELLS_IN_FLIGHT[kv] in fp64_counts, (kv, per_cell, sorted(fp64_counts)[-12:])

@@ -18,11 +18,17 @@ def _worker(rank, world, port, T, na, out_dir):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        from cvar_b200.distributed import gather_trajectories, shard_bounds
+        from cvar_b200.distributed import gather_blocks, gather_trajectories, shard_bounds
         full = torch.arange(na * T * 2, dtype=torch.int32).reshape(na, T, 2)
         lo, hi = shard_bounds(T, world, rank)
         got = gather_trajectories(full[:, lo:hi, :].contiguous(), T)
         torch.save(got, os.path.join(out_dir, f"r{rank}.pt"))
+        # the blocked layout the finalize kernels read without reshuffling: day d = blocks[d // per, :, d % per]
+        blocks = gather_blocks(full[:, lo:hi, :].contiguous(), T)
+        per = -(-T // world)
+        assert blocks.shape == (world, na, per, 2)
+        days = torch.arange(T)
+        assert torch.equal(blocks[days // per, :, days % per].permute(1, 0, 2), full)
     finally:
         dist.destroy_process_group()
 

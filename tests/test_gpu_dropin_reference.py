@@ -9,7 +9,7 @@ import textwrap
 
 import pytest
 
-from reference_install import BUILD_OBJECT, reference_env, reference_root
+from reference_runner import BUILD_OBJECT, reference_env, reference_root
 
 SCRIPT = BUILD_OBJECT + textwrap.dedent("""
     import contextlib, io, json

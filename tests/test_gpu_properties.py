@@ -336,3 +336,36 @@ def test_exact_zero_mass_exit_sets_its_status_bit(cuda_device):
     np.testing.assert_array_equal(res.var[0], tr.var)
     assert tr.iterations == 0 < max_iter and np.all(tr.zero_bits & 1)
     assert res.status[0] == _lib.STATUS_ZERO_EXIT_TAKEN
+
+
+@pytest.mark.gpu
+def test_blocked_finalize_equals_plain_finalize(cuda_device):
+    """cvar_finalize_blocked_device over [n_blocks][n_alpha][block][2] (what an all-gather of the ranks' blocks leaves
+    behind, ragged last block included) against the plain [n_alpha][T][2] layout."""
+    import torch
+    from cvar_b200 import synthetic as syn
+    from cvar_b200.backend import VarPlan
+    from cvar_b200.distributed import ShardedSolver
+
+    inp, alphas = syn.baseline_config("c2", T=23, n=128)
+    d_day = torch.from_numpy(inp.day_params()).cuda()
+    with VarPlan(inp, device=0) as plan:
+        traj = plan.solve_device(d_day, alphas)
+        var, case, iters = plan.finalize_device(traj, ptf_mean=0.25)
+        for block in (23, 12, 8, 5, 1):
+            nb = -(-inp.T // block)
+            blocks = torch.zeros((nb, len(alphas), block, 2), dtype=torch.int32, device="cuda")
+            for b in range(nb):
+                part = traj[:, b * block:(b + 1) * block]
+                blocks[b, :, : part.shape[1]] = part
+            v2, c2, i2 = plan.finalize_device(blocks, ptf_mean=0.25, T=inp.T)
+            assert torch.equal(v2, var) and torch.equal(c2, case) and torch.equal(i2, iters), block
+        # the overlapped single-rank solver: same numbers, results valid after synchronize()
+        solver = ShardedSolver(plan, inp.T, len(alphas), inp.T)
+        for _ in range(3):
+            v3, c3, i3 = solver.step(d_day, alphas, ptf_mean=0.25)
+        solver.synchronize()
+        torch.cuda.synchronize()
+        assert torch.equal(v3, var) and torch.equal(c3, case) and torch.equal(i3, iters)
+        phases = solver.phase_us(d_day, alphas, ptf_mean=0.25, repeats=2)
+        assert set(phases) == {"solve", "gather", "finalize"} and phases["solve"] > 0
