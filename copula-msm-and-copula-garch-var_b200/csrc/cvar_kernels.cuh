@@ -596,10 +596,7 @@ __device__ __forceinline__ StripResult block_reduce(const Smem& S, const Part& p
 // There is no per-strip barrier besides the one inside the block reduction, and the boundary arrays are
 // only ever touched by their owning thread.
 //
-// (Tried in round 2 and left out, see DESIGN.md section 10: a warp-synchronous "column sweep" in which groups of 2 / 4 / 8 /
-// 32 adjacent rows read the same column per trip -- one shared-memory wavefront per warp load instead of four, 10 % faster
-// in an isolated loop (tools/micro/cell_loop.cu) -- lost 2-4 % in the kernel: the rows of a group start and end at
-// different columns, and the ramps at both ends plus the warp votes per row block cost more than the wavefronts save.)
+// Blocks of long rows of the Plackett family take the column sweep below instead (sweep_rows).
 
 // Sum of the cells [s, e) of one row.
 template <int COPULA, bool FAST>
@@ -622,6 +619,79 @@ __device__ __forceinline__ double walk_row(const KernelParams& P, const Smem& S,
     for (; j < e; ++j) {
         const double2 v = S.in[j];
         acc[0] = row.template add_cell<FAST>(P, S, v.x, v.y, acc[0]);
+    }
+    double rowsum = acc[0];
+#pragma unroll
+    for (int c = 1; c < CIF; ++c) rowsum += acc[c];
+    return rowsum;
+}
+
+// Column sweep for blocks of LONG rows.  When every one of the warp's 32 rows holds at least SWEEP_MIN_ROW cells, groups
+// of G adjacent rows read the same column per trip (their 16-byte words steered into distinct banks, the groups skewed
+// so that they start together): a warp-wide column load then costs two shared-memory wavefronts instead of four (micro-
+// benchmark tools/micro/lds_patterns.cu).  Each lane walks what is left of its row at both ends by itself.
+// Measured per copula (1000 days, n = 2048; 2 alphas at n = 4096): the Plackett cell -- 8 FP64 and one column load per
+// cell, nothing else -- gains 3.1 % with pairs of rows (G = 2: 2.624 -> 2.542 ms; n = 4096: 9.30 -> 8.49 ms, -8.7 %) and 2.3 %
+// with G = 8; the Gaussian cell gains 7.3 % at n = 4096 (11.37 -> 10.53 ms with G = 2, 10.60 with G = 8); the Student-t cell,
+// whose loop is bound by issue slots (18 instructions per cell), loses 1-2 % with any G (c3 1.776 -> 1.79-1.81 ms, n = 4096
+// 10.48 -> 10.57-10.72 ms), so it keeps the plain walk.  Override with -DCVAR_SWEEP_<FAMILY>=0|2|4|8|16|32.
+#ifndef CVAR_SWEEP_GAUSSIAN
+#define CVAR_SWEEP_GAUSSIAN 2
+#endif
+#ifndef CVAR_SWEEP_STUDENT
+#define CVAR_SWEEP_STUDENT 0
+#endif
+#ifndef CVAR_SWEEP_PLACKETT
+#define CVAR_SWEEP_PLACKETT 2
+#endif
+#ifndef CVAR_SWEEP_MIN_ROW
+#define CVAR_SWEEP_MIN_ROW 128
+#endif
+template <int COPULA>
+struct SweepGroup {
+    static constexpr int value = COPULA == 0 ? CVAR_SWEEP_GAUSSIAN : (kv_is_student(COPULA) ? CVAR_SWEEP_STUDENT : CVAR_SWEEP_PLACKETT);
+};
+
+template <int COPULA, bool FAST>
+__device__ __forceinline__ double sweep_rows(const KernelParams& P, const Smem& S, const Row<COPULA>& row, int s, int e) {
+    constexpr int CIF = CellsInFlight<COPULA>::value;
+    constexpr unsigned FULL = 0xffffffffu;
+    constexpr int G = SweepGroup<COPULA>::value > 0 ? SweepGroup<COPULA>::value : 32, NG = 32 / G;
+    double acc[CIF];
+#pragma unroll
+    for (int c = 0; c < CIF; ++c) acc[c] = 0.0;
+    int off = 0;   // this lane reads column (trip - off)
+    if (G < 32) {
+        const int lane = threadIdx.x & 31, g = lane / G;
+        off = __shfl_sync(FULL, s, 0) - __shfl_sync(FULL, s, lane & ~(G - 1));
+        if (NG <= 8)
+            off += (g - off) & (NG - 1);
+        else   // 16 pairs: their words must fall on every 16-byte bank group exactly twice (offsets 2g + g/4 modulo 8)
+            off += ((2 * g + (g >> 2)) - off) & 7;
+    }
+    const int t0 = __reduce_max_sync(FULL, s + off);
+    const int t1 = __reduce_min_sync(FULL, e + off);
+    int left_end = s, right_begin = s;
+    if (t1 - t0 >= 2 * CIF) {
+        const int trips = (t1 - t0) / CIF;
+        const double2* col = S.in + (t0 - off);
+        for (int k = 0; k < trips; ++k, col += CIF) {
+            double2 v[CIF];
+#pragma unroll
+            for (int c = 0; c < CIF; ++c) v[c] = col[c];
+#pragma unroll
+            for (int c = 0; c < CIF; ++c) acc[c] = row.template add_cell<FAST>(P, S, v[c].x, v[c].y, acc[c]);
+        }
+        left_end = t0 - off;
+        right_begin = t0 - off + trips * CIF;
+    }
+#pragma unroll 1
+    for (int seg = 0; seg < 2; ++seg) {   // the ends are short: a plain loop
+        const int je = seg ? e : left_end;
+        for (int j = seg ? right_begin : s; j < je; ++j) {
+            const double2 v = S.in[j];
+            acc[0] = row.template add_cell<FAST>(P, S, v.x, v.y, acc[0]);
+        }
     }
     double rowsum = acc[0];
 #pragma unroll
@@ -673,6 +743,20 @@ __device__ StripResult strip_pass(const KernelParams& P, const Smem& S, const Pa
                     }
                 }
             }
+        }
+        if (SweepGroup<COPULA>::value > 0 && __all_sync(0xffffffffu, e - s >= CVAR_SWEEP_MIN_ROW)) {   // every lane arrives here
+            Row<COPULA> srow;
+            srow.load(P, S, i);
+            bool sfast = false;
+            if (kv_pow_degree(COPULA) > 0 && POW_FAST_MODE > 0 && P.pow_octaves > 0) {
+                sfast = L.day_fast;
+                if (!sfast)
+                    sfast = !__any_sync(0xffffffffu, !(fmax(srow.quad_form(S.in[s].x), srow.quad_form(S.in[e - 1].x)) < P.pow_fast_limit));
+            }
+            const double ssum = (kv_pow_degree(COPULA) > 0 && POW_FAST_MODE > 0 && sfast)
+                                    ? sweep_rows<COPULA, true>(P, S, srow, s, e) : sweep_rows<COPULA, false>(P, S, srow, s, e);
+            total = fma(srow.fac, ssum, total);
+            continue;
         }
         if (e <= s) continue;
         Row<COPULA> row;

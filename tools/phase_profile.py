@@ -11,7 +11,8 @@ from cvar_b200 import synthetic as syn
 from cvar_b200.backend import VarPlan
 
 name = sys.argv[1] if len(sys.argv) > 1 else "c3"
-inp, alphas = syn.baseline_config(name)
+T = int(sys.argv[2]) if len(sys.argv) > 2 else None
+inp, alphas = syn.baseline_config(name, T=T)
 alphas = alphas[:1]
 plan = VarPlan(inp, device=0)
 d = torch.from_numpy(inp.day_params()).cuda()
