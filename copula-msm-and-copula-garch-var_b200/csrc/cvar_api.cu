@@ -379,6 +379,8 @@ extern "C" {
 
 int cvar_abi_version(void) { return CVAR_ABI_VERSION; }
 
+int cvar_check_dim(int32_t dim) { return dim == 2 ? CVAR_OK : CVAR_ERR_DIM; }
+
 void cvar_desc_default(cvar_desc_t* d) {
     if (!d) return;
     std::memset(d, 0, sizeof(*d));
@@ -413,6 +415,7 @@ const char* cvar_strerror(int status) {
         case CVAR_ERR_NO_DEVICE: return "no usable CUDA device (this library has no CPU fallback)";
         case CVAR_ERR_ABI: return "cvar_desc_t struct_size / abi_version mismatch";
         case CVAR_ERR_SMEM: return "grid too large for the shared memory of one SM";
+        case CVAR_ERR_DIM: return "only two-asset portfolios are supported (the reference's dim >= 3 grid does not yield probabilities; see cvar.h)";
         case CVAR_ERR_TABLE: return "Student-t quantile table missed its accuracy budget for this nu (plan refused)";
         default: break;
     }

@@ -49,6 +49,7 @@ _PD = C.POINTER(C.c_double)
 _PROTOTYPES = {
     "cvar_abi_version": (C.c_int, []),
     "cvar_desc_default": (None, [C.POINTER(CvarDesc)]),
+    "cvar_check_dim": (C.c_int, [C.c_int32]),
     "cvar_strerror": (C.c_char_p, [C.c_int]),
     "cvar_plan_create": (C.c_int, [C.POINTER(CvarDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]),
     "cvar_plan_destroy": (C.c_int, [C.c_void_p]),
@@ -104,6 +105,13 @@ def load(path: str | Path | None = None):
     if path is None:
         _lib = lib
     return lib
+
+
+def check_dim(dim: int):
+    """NotImplementedError (with the library's own message) for portfolios the backend refuses: dim != 2."""
+    status = load().cvar_check_dim(int(dim))
+    if status != 0:
+        raise NotImplementedError(f"dim = {dim}: {load().cvar_strerror(status).decode()} (status {status})")
 
 
 def check(status: int, where: str):

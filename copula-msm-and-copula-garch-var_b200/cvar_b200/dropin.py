@@ -18,6 +18,7 @@ from __future__ import annotations
 
 import numpy as np
 
+from . import _lib
 from .backend import VarPlan
 from .inputs import HotPathInputs
 
@@ -43,8 +44,7 @@ def inputs_from_reference_object(v) -> HotPathInputs:
     else:
         kw["probs"] = np.asarray(v.integrations_params_t[0], float)
         kw["sigma_states"] = np.asarray(v.integrations_params_static, float)
-    if int(getattr(v, "dim", 2)) != 2:
-        raise NotImplementedError("the B200 backend covers two-asset portfolios")
+    _lib.check_dim(int(getattr(v, "dim", 2)))
     return HotPathInputs(**kw)
 
 

@@ -20,6 +20,7 @@ from collections import OrderedDict
 
 import numpy as np
 
+from cvar_b200 import _lib
 from cvar_b200.backend import VarPlan
 from cvar_b200.inputs import HotPathInputs
 
@@ -76,8 +77,8 @@ def calc_grids_and_integrals_results(
                                      ):
     """Strip mass of every day t in range(T) for its bounds `unique_var_values[unique_indices[t]]` = (lower, upper):
     np.ndarray[T], what the reference's function of the same name returns (calc_integral.py:8-119)."""
-    if int(dim) != 2 or len(weights) != 2:
-        raise NotImplementedError("the B200 backend covers two-asset portfolios (dim == 2)")
+    _lib.check_dim(int(dim))
+    _lib.check_dim(len(weights))
     family = copula_family_of(copula_density, unpack_copula_params, copula_params)
     bounds = np.asarray(unique_var_values, dtype=float).reshape(-1, 2)[np.asarray(unique_indices).reshape(-1)]
     if bounds.shape[0] != int(T):

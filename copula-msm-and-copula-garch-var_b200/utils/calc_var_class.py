@@ -9,6 +9,7 @@ import time
 
 import numpy as np
 
+from cvar_b200 import _lib
 from cvar_b200.backend import VarPlan
 from cvar_b200.inputs import HotPathInputs
 from utils.calc_var_ABC import OutOfScopeStage
@@ -38,8 +39,8 @@ def hot_path_inputs_from_attributes(obj, copula_family=None, marginal_family=Non
     else:
         kw["probs"] = np.asarray(obj.integrations_params_t[0], float)
         kw["sigma_states"] = np.asarray(obj.integrations_params_static, float)
-    if int(getattr(obj, "dim", 2)) != 2 or len(kw["weights"]) != 2:
-        raise NotImplementedError("the B200 backend covers two-asset portfolios (every BASELINE configuration)")
+    _lib.check_dim(int(getattr(obj, "dim", 2)))
+    _lib.check_dim(len(kw["weights"]))
     return HotPathInputs(**kw)
 
 

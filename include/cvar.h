@@ -69,6 +69,7 @@ extern "C" {
 #define CVAR_ERR_NO_DEVICE (-6)     /* no usable CUDA device (there is no CPU fallback)  */
 #define CVAR_ERR_ABI (-7)           /* struct_size / abi_version mismatch                */
 #define CVAR_ERR_SMEM (-8)          /* grid too large for the shared memory of one SM    */
+#define CVAR_ERR_DIM (-10)          /* portfolio dimension other than 2 (see cvar_check_dim)           */
 #define CVAR_ERR_TABLE (-9)         /* Student-t: the per-plan quantile table is less accurate than 1e-11 for this nu
                                        (checked against the iterative routine at plan creation); the plan is refused */
 
@@ -145,6 +146,18 @@ typedef struct cvar_plan_info {
  *   CVAR_NO_SEGMENT_GUESS=1    row boundaries by plain bisection even on a piecewise-uniform axis
  * The Python loader additionally honours CVAR_B200_LIB=<path to an alternative libcvar_b200.so>.
  */
+
+/*
+ * Portfolio dimension.  DECISION: this backend solves TWO-asset portfolios and refuses anything else with CVAR_ERR_DIM;
+ * it does not reproduce the reference's recursive grid for dim >= 3 "as written".  Reason: run unmodified on a three-asset
+ * Gaussian + GARCH example (n = 24), the reference's create_nested_grid (utils/calc_integral/create_grids.py:125-171)
+ * returns "probabilities" F(0.5) = 3.45 and F(20) = 4.32 -- its recursion multiplies every inner level by the full step
+ * product -- so there is no meaningful parity target, and every BASELINE configuration has two assets.  cvar_desc_t
+ * therefore carries exactly two weights; hosts that hold a `dim` (the reference's ValueAtRiskCalcualtion.dim,
+ * utils/calc_var_class.py:31) check it here and surface the refusal (the Python mirror and `dropin` raise
+ * NotImplementedError with this status' text).
+ */
+int cvar_check_dim(int32_t dim);
 
 /* Fill *desc with the reference's defaults (everything except copula/marginal/n/q/params). */
 void cvar_desc_default(cvar_desc_t* desc);

@@ -120,3 +120,14 @@ def test_issued_fp64_per_cell_constants_match_the_sass():
         fp64_counts = {int(m.group(1)) for m in re.finditer(r"FP64\s+(\d+),", loops)}
         for per_cell in {fast, slow}:
             assert per_cell * CELLS_IN_FLIGHT[kv] in fp64_counts, (kv, per_cell, sorted(fp64_counts)[-12:])
+
+
+def test_dimension_decision_is_a_status_code(lib):
+    """f4: portfolios with dim != 2 are refused, explicitly (cvar_check_dim / CVAR_ERR_DIM), in the C ABI and above it."""
+    from cvar_b200 import _lib
+    assert lib.cvar_check_dim(2) == 0
+    for dim in (1, 3, 5):
+        assert lib.cvar_check_dim(dim) == -10
+    assert b"two-asset" in lib.cvar_strerror(-10)
+    with pytest.raises(NotImplementedError, match="two-asset"):
+        _lib.check_dim(3)
