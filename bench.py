@@ -332,13 +332,15 @@ def run_b200(args, world, rank, local_rank):
     torch.cuda.synchronize()
     kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in kev]))
     cells = torch.zeros((na, inp.T), dtype=torch.int64, device=dev)
+    plan.evaluated_cells(reset=True)
     plan.solve_device(d_day, alphas, traj=traj, cells=cells)
     torch.cuda.synchronize()
+    cells_evaluated = plan.evaluated_cells(reset=True)     # strips shared between the alphas of a day are evaluated once
     cells_np = cells.cpu().numpy()
     flops_launch = algorithmic_flops(inp.copula, inp.marginal, inp.q, inp.n, cells_np)
     achieved_tf = flops_launch / (kernel_ms * 1e-3) / 1e12
     peak_tf, peak_ms = fp64_peak_tflops(local_rank, 100.0)
-    cell_frac = cell_fp64_pipe_fraction(info.kernel_variant, info.pow_octaves, cells_np, kernel_ms * 1e-3, peak_tf)
+    cell_frac = cell_fp64_pipe_fraction(info.kernel_variant, info.pow_octaves, cells_evaluated, kernel_ms * 1e-3, peak_tf)
 
     # ---- phases and the pipelined variant ---------------------------------------------------------------
     solver = ShardedSolver(plan, T_total, na, inp.T)
@@ -437,11 +439,11 @@ def run_b200(args, world, rank, local_rank):
             "kernel_ms": kernel_ms, "algorithmic_flops_per_launch": flops_launch,
             "cell_pipe_frac": cell_frac,
             "issued_fp64_per_cell": issued_fp64_per_cell(info.kernel_variant, info.pow_octaves),
-            "cells_per_solve_mean": float(cells_np.mean()),
+            "cells_per_solve_mean": float(cells_np.mean()), "cells_evaluated_per_launch": int(cells_evaluated),
             "frac_note": "frac = algorithmic flops (SURVEY 8(d): 80 per Student cell, exp = 30, log = 42) / time / measured DFMA "
                          "peak; it exceeds 1 because the kernel issues far fewer FP64 instructions per cell than that convention "
-                         "charges.  cell_pipe_frac = cells x ISSUED FP64 instructions per cell (SASS count, tests/test_abi.py) / "
-                         "pipe slots in kernel_ms: a lower bound of ncu's sm__pipe_fp64_cycles_active (profiles/), which also "
+                         "charges.  cell_pipe_frac = cells really evaluated (strips shared between alphas count once) x ISSUED FP64 "
+                         "instructions per cell (SASS count, tests/test_abi.py) / pipe slots in kernel_ms: a lower bound of ncu's sm__pipe_fp64_cycles_active (profiles/), which also "
                          "sees the axis stage, row set-up and masked lanes",
             "peak_source": f"measured in this run: dependency-free DFMA micro-benchmark, {peak_ms:.0f} ms "
                            "(MEASURED_PEAKS.json has no FP64 entry; nominal 148 SM x 64 lanes x 2 x 1.965 GHz = 37.2)",

@@ -610,8 +610,10 @@ int cvar_plan_create(const cvar_desc_t* desc, const double* x, const double* dx,
 
     PLAN_TRY(cudaMalloc(&p->d_x, sizeof(double) * n));
     PLAN_TRY(cudaMalloc(&p->d_dx, sizeof(double) * n));
-    PLAN_TRY(cudaMalloc(&p->d_k, sizeof(int) * 2 * CVAR_MAX_ALPHA));
-    PLAN_TRY(cudaMemsetAsync(p->d_k, 0, sizeof(int) * 2 * CVAR_MAX_ALPHA, p->stream));
+    // [2][CVAR_MAX_ALPHA] ints (iteration counts, status words), then the 8-byte evaluated-cells counter
+    PLAN_TRY(cudaMalloc(&p->d_k, sizeof(int) * 2 * CVAR_MAX_ALPHA + sizeof(unsigned long long)));
+    PLAN_TRY(cudaMemsetAsync(p->d_k, 0, sizeof(int) * 2 * CVAR_MAX_ALPHA + sizeof(unsigned long long), p->stream));
+    p->kp.evaluated_cells = reinterpret_cast<unsigned long long*>(p->d_k + 2 * CVAR_MAX_ALPHA);
     PLAN_TRY(cudaMemcpyAsync(p->d_x, x, sizeof(double) * n, cudaMemcpyHostToDevice, p->stream));
     PLAN_TRY(cudaMemcpyAsync(p->d_dx, dx, sizeof(double) * n, cudaMemcpyHostToDevice, p->stream));
     if (desc->marginal == CVAR_MARGINAL_MIXTURE) {
@@ -875,6 +877,17 @@ int cvar_finalize_blocked_device(cvar_plan_t* p, const uint32_t* traj, int64_t T
     if (rc) return rc;
     if (iterations_out)
         CU_TRY(cudaMemcpyAsync(iterations_out, p->d_k, sizeof(int) * n_alpha, cudaMemcpyDeviceToDevice, st));
+    return CVAR_OK;
+}
+
+int cvar_evaluated_cells_host(cvar_plan_t* p, uint64_t* total_out, int reset) {
+    if (!p || !total_out) return CVAR_ERR_NULL;
+    DeviceGuard guard(p->device);
+    CU_TRY(cudaDeviceSynchronize());   // launches on any stream
+    unsigned long long v = 0;
+    CU_TRY(cudaMemcpy(&v, p->kp.evaluated_cells, sizeof(v), cudaMemcpyDeviceToHost));
+    if (reset) CU_TRY(cudaMemset(p->kp.evaluated_cells, 0, sizeof(v)));
+    *total_out = v;
     return CVAR_OK;
 }
 

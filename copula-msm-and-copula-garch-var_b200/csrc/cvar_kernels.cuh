@@ -97,6 +97,8 @@ struct KernelParams {
     const double* tq_table;      // student only
     const double* state_cdf;     // mixture: Phi(x_i / sigma_{a,s}), [2][q][n]
     const double* state_pdf;     // mixture: N(x_i; 0, sigma_{a,s}), [2][q][n]
+    unsigned long long* evaluated_cells;   // plan-wide counter of the cells the launches really evaluated (strips shared
+                                           // between the alphas of a day are evaluated once): the roofline's numerator
 };
 
 struct AlphaSet {
@@ -790,7 +792,8 @@ __device__ __forceinline__ StripResult strip_memo(const KernelParams& P, const S
                                                   bool use_memo, bool remember, int memo_visible, int& memo_n,
                                                   double a, double b,
                                                   double q_new, u16* cnew, const u16* slo, const u16* shi,
-                                                  const u16* ca, const u16* cb, bool poison_mode) {
+                                                  const u16* ca, const u16* cb, bool poison_mode,
+                                                  unsigned long long& evaluated) {
     if (use_memo) {
         for (int k = 0; k < memo_visible; ++k) {
             const double* e = S.memo + 4 * k;
@@ -805,6 +808,7 @@ __device__ __forceinline__ StripResult strip_memo(const KernelParams& P, const S
         }
     }
     const StripResult r = strip_pass<COPULA>(P, S, pt, L, parity, q_new, cnew, slo, shi, ca, cb, poison_mode);
+    evaluated += r.cells;
     if (use_memo && remember && memo_n < MEMO_SIZE) {
         if (threadIdx.x == 0) {
             double* e = S.memo + 4 * memo_n;
@@ -868,6 +872,7 @@ solve_kernel(KernelParams P, const double* __restrict__ day_params, long long da
     const bool poison_mode = (COPULA != 2) && (P.marginal == 1) && ((P.compat & 4u) != 0);
     int parity = 0;
 
+    unsigned long long evaluated = 0;   // cells this CTA's cluster really evaluated (all alphas)
     bool have_f3 = false;
     StripResult f3 = {0.0, 0u, false};
     const bool use_memo = A.n_alpha > 1;
@@ -882,6 +887,7 @@ solve_kernel(KernelParams P, const double* __restrict__ day_params, long long da
         if (!have_f3) {
             f3 = strip_pass<COPULA>(P, S, pt, L, parity, P.first, S.c[0], nullptr, nullptr, nullptr, S.c[0], poison_mode);
             have_f3 = true;
+            evaluated += f3.cells;
         } else {
             count_rows(P, S, pt, P.first, S.c[0], nullptr, nullptr);
         }
@@ -893,10 +899,10 @@ solve_kernel(KernelParams P, const double* __restrict__ day_params, long long da
         StripResult s2;
         if (lo2 == P.first)   // strip (first, second_hi]: new upper boundary, searched above c[0]
             s2 = strip_memo<COPULA>(P, S, pt, L, parity, use_memo, true, memo_visible, memo_n, lo2, hi2, hi2, S.c[1], S.c[0], nullptr,
-                                    S.c[0], S.c[1], poison_mode);
+                                    S.c[0], S.c[1], poison_mode, evaluated);
         else                  // strip (second_lo, first]: new lower boundary, searched below c[0]
             s2 = strip_memo<COPULA>(P, S, pt, L, parity, use_memo, true, memo_visible, memo_n, lo2, hi2, lo2, S.c[1], nullptr, S.c[0],
-                                    S.c[1], S.c[0], poison_mode);
+                                    S.c[1], S.c[0], poison_mode, evaluated);
         ncell += s2.cells;
         double R = (lo2 == P.first) ? f3.mass + s2.mass : f3.mass - s2.mass;
         if ((P.compat & 2u) == 0 && lo2 == P.first) prev_upper = hi2;  // intended behaviour: R = F(hi2)
@@ -931,7 +937,7 @@ solve_kernel(KernelParams P, const double* __restrict__ day_params, long long da
                 const double mid = (lo + hi) / 2;
                 const double a = stack ? lo : mid, b = stack ? mid : hi;
                 const StripResult s = strip_memo<COPULA>(P, S, pt, L, parity, use_memo, k < MEMO_PER_ALPHA - 1, memo_visible, memo_n, a, b,
-                                                         mid, cm, cl, ch, stack ? cl : cm, stack ? cm : ch, poison_mode);
+                                                         mid, cm, cl, ch, stack ? cl : cm, stack ? cm : ch, poison_mode, evaluated);
                 ncell += s.cells;
                 const double r_prev = R;
                 R = (a == prev_upper) ? R + s.mass : R - s.mass;  // adjust_integral (:241-246)
@@ -960,6 +966,7 @@ solve_kernel(KernelParams P, const double* __restrict__ day_params, long long da
 #endif
         }
     }
+    if (P.evaluated_cells && threadIdx.x == 0 && pt.rank == 0) atomicAdd(P.evaluated_cells, evaluated);
     // no CTA may retire while a peer can still read its partial sums
     if (CLUSTER) cooperative_groups::this_cluster().sync();
 }

@@ -59,6 +59,7 @@ _PROTOTYPES = {
     "cvar_strip_mass_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "cvar_solve_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "cvar_finalize_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "cvar_evaluated_cells_host": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.c_int]),
     "cvar_finalize_blocked_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "cvar_finalize_status_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     "cvar_finalize_status_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32]),

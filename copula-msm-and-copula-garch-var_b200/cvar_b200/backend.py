@@ -157,6 +157,13 @@ class VarPlan:
         return SolveResult(var=var, case=case, cells=cells, iterations=iters, kernel_ms=float(self.info().last_kernel_ms),
                            status=self.last_status(na))
 
+    def evaluated_cells(self, reset: bool = True) -> int:
+        """Cells the plan's solve launches really evaluated since the last reset (cvar_evaluated_cells_host): the
+        numerator of the issued-instruction roofline; strips shared between the alphas of a day count once."""
+        total = C.c_uint64()
+        _lib.check(self._lib.cvar_evaluated_cells_host(self._h, C.byref(total), int(bool(reset))), "cvar_evaluated_cells_host")
+        return int(total.value)
+
     def last_status(self, n_alpha: int = 1) -> np.ndarray:
         """CVAR_STATUS_* words of the plan's last finalize, one per alpha (cvar_finalize_status_host)."""
         out = np.zeros(int(n_alpha), dtype=np.int32)

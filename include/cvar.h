@@ -245,6 +245,14 @@ int cvar_finalize_blocked_device(cvar_plan_t* plan, const uint32_t* traj, int64_
                                  int32_t* case_out, int32_t* iterations_out, void* stream);
 
 /*
+ * Work counter for the roofline: the number of grid cells the plan's solve launches really evaluated since the last
+ * reset, summed over days and alphas.  Differs from the `cells` output of cvar_solve_* (the cells of the reference's own
+ * strip scheme, per solve) when several alphas are solved together: strips they have in common are evaluated once.
+ * Synchronises the device.  (No counterpart in the reference.)
+ */
+int cvar_evaluated_cells_host(cvar_plan_t* plan, uint64_t* total_out, int reset);
+
+/*
  * Status words of the plan's LAST finalize (cvar_finalize_device, or the finalize inside cvar_solve_host), one per alpha:
  *   CVAR_STATUS_ZERO_EXIT_TAKEN      the iteration count K was cut because the running mass of EVERY day of the batch was
  *                                    exactly 0 after iteration K -- the reference's early exit (calc_var_class.py:293-295)

@@ -369,3 +369,27 @@ def test_blocked_finalize_equals_plain_finalize(cuda_device):
         assert torch.equal(v3, var) and torch.equal(c3, case) and torch.equal(i3, iters)
         phases = solver.phase_us(d_day, alphas, ptf_mean=0.25, repeats=2)
         assert set(phases) == {"solve", "gather", "finalize"} and phases["solve"] > 0
+
+
+@pytest.mark.gpu
+def test_evaluated_cell_counter(cuda_device):
+    """cvar_evaluated_cells_host: with one alpha it equals the sum of the per-solve cell counters; with two alphas it is
+    smaller than their sum (shared strips are evaluated once) and at least the larger alpha's share."""
+    import torch
+    from cvar_b200 import synthetic as syn
+    from cvar_b200.backend import VarPlan
+
+    inp, alphas = syn.baseline_config("c2", T=11, n=192)
+    d_day = torch.from_numpy(inp.day_params()).cuda()
+    with VarPlan(inp, device=0) as plan:
+        cells = torch.zeros((1, inp.T), dtype=torch.int64, device="cuda")
+        plan.evaluated_cells(reset=True)
+        plan.solve_device(d_day, alphas[:1], cells=cells)
+        one = plan.evaluated_cells(reset=True)
+        assert one == int(cells.sum().item()) > 0
+        assert plan.evaluated_cells(reset=True) == 0
+        cells2 = torch.zeros((2, inp.T), dtype=torch.int64, device="cuda")
+        plan.solve_device(d_day, alphas, cells=cells2)
+        both = plan.evaluated_cells(reset=False)
+        per_alpha = cells2.sum(dim=1).cpu().numpy()
+        assert per_alpha.max() <= both < per_alpha.sum()
