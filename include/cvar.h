@@ -144,6 +144,11 @@ typedef struct cvar_plan_info {
  *                              stays resident (n >= 1024), else 1
  *   CVAR_STUDENT_GENERIC=1     Student-t plans use the generic log2/exp2 cell instead of the table-assisted power cell
  *   CVAR_NO_SEGMENT_GUESS=1    row boundaries by plain bisection even on a piecewise-uniform axis
+ *   CVAR_POW_OCTAVES=0..8      octaves of the Student-t cell's one-lookup power table (default: as many as fit without
+ *                              costing the SM a resident warp, none below four)
+ *   CVAR_CHUNK_DAYS=N          days per launch of the solve kernel a new plan reserves scratch for (cvar_plan_reserve)
+ *   CVAR_TQ_BUDGET=x           accuracy budget of the Student-t quantile table (default 1e-11; tests force a refusal)
+ * Read by the Python layers: CVAR_BACKEND=b200|reference (factory default).
  * The Python loader additionally honours CVAR_B200_LIB=<path to an alternative libcvar_b200.so>.
  */
 
