@@ -326,7 +326,11 @@ int launch_solve_kernel(cvar_plan* p, int cluster, int threads, int64_t units, c
 // A batch runs as chunks of at most chunk_days days (the size of the launch-order scratch): order, solve kernel, on `st`.
 // (Tried and left out: running the cheapest ~20 % of a chunk -- the last CTAs of the launch order -- as 2-CTA clusters in a
 // second kernel on another stream, so that the tail of the launch is made of shorter units.  c3: 1.78 -> 1.82-1.91 ms for
-// 100-400 tail days; the cluster barrier per strip and the second axis stage cost more than the idle SMs of the tail.)
+// 100-400 tail days; the cluster barrier per strip and the second axis stage cost more than the idle SMs of the tail.
+// Also tried: the remainder of the chunk modulo the resident CTA slots (112 of 1000 days) as CTAs of twice the threads, one
+// per SM: 1.776 -> 1.804 ms -- a wide CTA only starts on an SM once BOTH of its slots have drained.  A simulation of the
+// launch with the measured per-day costs gives a makespan of 1.20 x the ideal for 1000 days on 296 slots with ANY order
+// (1.07 for 2000 days, 1.02 for 8000): the loss is the quantisation of 3.4 waves, not the order.)
 int launch_solve(cvar_plan* p, const double* d_day, int64_t T, const AlphaSet& A, uint32_t* d_traj, double* d_mass,
                  unsigned long long* d_cells, cudaStream_t st) {
     for (int64_t c0 = 0; c0 < T; c0 += p->chunk_days) {
