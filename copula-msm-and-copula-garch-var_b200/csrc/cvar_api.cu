@@ -52,6 +52,8 @@ struct cvar_plan {
     void* d_ws;
     size_t ws_bytes;
     int* d_k;  // [2][CVAR_MAX_ALPHA]: iteration counts, then status words of the last finalize
+    int h_k[2 * CVAR_MAX_ALPHA];   // host copy of d_k after a *_host solve (one D2H for iterations and status)
+    bool status_on_host;
     // launch-order scratch (keys, indices, sorted copies, cub temp), sized by cvar_plan_reserve for `chunk_days` days and
     // never grown inside a *_device call
     int64_t chunk_days;
@@ -365,6 +367,12 @@ int launch_finalize(cvar_plan* p, const uint32_t* d_traj, int64_t T, int64_t blo
     F.ptf_mean = ptf_mean;
     for (int i = 0; i < CVAR_MAX_ALPHA; ++i) F.forced[i] = (forced && i < n_alpha) ? forced[i] : -1;
     const long long blk = std::max<int64_t>(block, 1);
+    p->status_on_host = false;
+    if (T <= 4096) {   // small batch: one launch instead of two
+        finalize_small_kernel<<<n_alpha, 256, 0, st>>>(F, d_traj, (long long)T, blk, n_alpha, p->d_k, p->d_k + CVAR_MAX_ALPHA,
+                                                       d_var, d_case);
+        return (int)cudaGetLastError();
+    }
     finalize_reduce_kernel<<<n_alpha, 1024, 0, st>>>(F, d_traj, (long long)T, blk, n_alpha, p->d_k, p->d_k + CVAR_MAX_ALPHA);
     CU_TRY(cudaGetLastError());
     const long long total = (long long)T * n_alpha;
@@ -906,6 +914,10 @@ int cvar_finalize_status_device(cvar_plan_t* p, int32_t* status_out, int32_t n_a
 int cvar_finalize_status_host(cvar_plan_t* p, int32_t* status_out, int32_t n_alpha) {
     if (!p || !status_out) return CVAR_ERR_NULL;
     if (n_alpha < 1 || n_alpha > CVAR_MAX_ALPHA) return CVAR_ERR_SIZE;
+    if (p->status_on_host) {   // the last finalize was a *_host solve: its status words came back with the results
+        std::memcpy(status_out, p->h_k + CVAR_MAX_ALPHA, sizeof(int) * n_alpha);
+        return CVAR_OK;
+    }
     DeviceGuard guard(p->device);
     CU_TRY(cudaMemcpyAsync(status_out, p->d_k + CVAR_MAX_ALPHA, sizeof(int) * n_alpha, cudaMemcpyDeviceToHost, p->stream));
     CU_TRY(cudaStreamSynchronize(p->stream));
@@ -951,8 +963,10 @@ int cvar_solve_host(cvar_plan_t* p, const double* day_params, int64_t T, const d
         if (case_out) CU_TRY(cudaMemcpyAsync(case_out, d_cas, sizeof(int32_t) * T * na, cudaMemcpyDeviceToHost, p->stream));
         if (cells_out) CU_TRY(cudaMemcpyAsync(cells_out, d_cel, sizeof(uint64_t) * T * na, cudaMemcpyDeviceToHost, p->stream));
     }
-    if (iterations_out) CU_TRY(cudaMemcpyAsync(iterations_out, p->d_k, sizeof(int) * n_alpha, cudaMemcpyDeviceToHost, p->stream));
+    CU_TRY(cudaMemcpyAsync(p->h_k, p->d_k, sizeof(p->h_k), cudaMemcpyDeviceToHost, p->stream));   // iterations + status
     CU_TRY(cudaStreamSynchronize(p->stream));
+    p->status_on_host = true;
+    if (iterations_out) std::memcpy(iterations_out, p->h_k, sizeof(int) * n_alpha);
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, p->ev0, p->ev1) == cudaSuccess) p->last_kernel_ms = ms;
     return CVAR_OK;

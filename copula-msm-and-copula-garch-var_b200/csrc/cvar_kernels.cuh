@@ -1101,6 +1101,70 @@ __global__ void finalize_reduce_kernel(FinalizeParams F, const unsigned* __restr
     }
 }
 
+// Small batches: reduction and reconstruction in ONE launch, one block per alpha (a launch costs more than either kernel).
+__global__ void __launch_bounds__(256) finalize_small_kernel(FinalizeParams F, const unsigned* __restrict__ traj, long long T,
+                                                             long long block, int n_alpha, int* __restrict__ k_out,
+                                                             int* __restrict__ status_out, double* __restrict__ var_out,
+                                                             int* __restrict__ case_out) {
+    __shared__ int s_need, s_firm, s_fragile, s_k;
+    __shared__ unsigned s_nonzero;
+    const int ia = blockIdx.x;
+    if (threadIdx.x == 0) { s_need = 0; s_nonzero = 0; s_firm = 0; s_fragile = 0; }
+    __syncthreads();
+    int need = 0, firm = 0, fragile = 0;
+    unsigned nonzero = 0;
+    const unsigned mask = (F.max_iter >= 32) ? 0xffffffffu : ((1u << F.max_iter) - 1u);
+    for (long long d = threadIdx.x; d < T; d += blockDim.x) {
+        const long long o = traj_index(block, n_alpha, ia, d);
+        const unsigned w0 = traj[2 * o], w1 = traj[2 * o + 1];
+        const unsigned kase = (w0 >> 28) & 7u;
+        if (kase < 4) {
+            need = max(need, F.need[kase]);
+            nonzero |= (~w1) & mask;
+            if (w0 & TRAJ_FRAGILE_BIT) fragile = 1;
+            else if ((w1 & mask) == 0u) firm = 1;
+        } else {
+            nonzero |= mask;
+            firm = 1;
+        }
+    }
+    atomicMax(&s_need, need);
+    atomicOr(&s_nonzero, nonzero);
+    if (firm) atomicOr(&s_firm, 1);
+    if (fragile) atomicOr(&s_fragile, 1);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int K = s_need, status = 0;
+        const unsigned allzero = (~s_nonzero) & mask;
+        if (T > 0 && allzero && __ffs(allzero) - 1 < K) {
+            K = __ffs(allzero) - 1;
+            status |= STATUS_ZERO_EXIT_TAKEN;
+        }
+        if (T > 0 && s_fragile && !s_firm) status |= STATUS_ZERO_EXIT_AMBIGUOUS;
+        if (F.forced[ia] >= 0) K = F.forced[ia];
+        s_k = min(K, F.max_iter);
+        k_out[ia] = s_k;
+        status_out[ia] = status;
+    }
+    __syncthreads();
+    const int K = s_k;
+    for (long long d = threadIdx.x; d < T; d += blockDim.x) {
+        const unsigned w0 = traj[2 * traj_index(block, n_alpha, ia, d)];
+        const unsigned kase = (w0 >> 28) & 7u;
+        double v = NAN;
+        if (kase < 4) {
+            double lo = F.lo[kase], hi = F.hi[kase];
+            for (int k = 0; k < K; ++k) {
+                const double mid = (lo + hi) / 2;
+                if ((w0 >> k) & 1u) lo = mid; else hi = mid;
+            }
+            v = (lo + hi) / 2 + F.ptf_mean;
+        }
+        var_out[(long long)ia * T + d] = v;
+        if (case_out) case_out[(long long)ia * T + d] = (int)kase;
+    }
+}
+
 __global__ void finalize_apply_kernel(FinalizeParams F, const unsigned* __restrict__ traj, long long T, long long block,
                                       int n_alpha, const int* __restrict__ k_in, double* __restrict__ var_out,
                                       int* __restrict__ case_out) {

@@ -134,8 +134,8 @@ class VarPlan:
         """All (day, alpha) solves of a batch: `calc_var` for every alpha (calc_var_class.py:95-177).
 
         ``out`` may be a preallocated (n_alpha, T) float64 array (e.g. pinned memory) receiving the VaR levels.
-        ``details=False`` skips the bracket ids and cell counters (`case` and `cells` of the result are None): nothing
-        but the VaR vector and the iteration counts is copied back.
+        ``details=False`` skips the bracket ids, cell counters, status words and kernel time (those fields of the result are
+        None / NaN): nothing but the VaR vector and the iteration counts is copied back.
         """
         alphas = _f64(np.atleast_1d(alphas))
         na = alphas.shape[0]
@@ -154,6 +154,8 @@ class VarPlan:
         st = self._lib.cvar_solve_host(self._h, _ptr(day), T, _ptr(alphas), na, _ptr(forced), float(ptf_mean),
                                        _ptr(var), _ptr(case), _ptr(cells), _ptr(iters))
         _lib.check(st, "cvar_solve_host")
+        if not details:   # the lean path: nothing beyond the VaR levels and the iteration counts is fetched
+            return SolveResult(var=var, case=None, cells=None, iterations=iters, kernel_ms=float("nan"), status=None)
         return SolveResult(var=var, case=case, cells=cells, iterations=iters, kernel_ms=float(self.info().last_kernel_ms),
                            status=self.last_status(na))
 
