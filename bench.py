@@ -15,7 +15,8 @@ Prints ONE JSON line (rank 0):
                 measured in the same run, and `cell_pipe_frac`, the pipe share of the ISSUED FP64 instructions of the cells
   strong        (default line) a second, shorter measurement with the total number of days fixed at 8000
   phases_us     solve / all-gather / finalize of one step, timed one after the other
-  pipelined     throughput with a step's collective + finalize overlapped with the next step's solve (ShardedSolver)
+  pipelined     throughput with two batches in flight on two streams (ShardedSolver): the next step's solve covers a
+                step's collective + finalize and the partly idle end of its solve launch
   cpu_baseline  the NumPy/SciPy oracle port on this box's host cores (N = 1), plus -- when a reference install is present
                 (baseline/_ref) -- the UNMODIFIED reference's calc_var timed on BASELINE configs[0]
   parity        max |dVaR| against the oracle on a sample of days spread over all shards, exceedance counts
@@ -343,7 +344,8 @@ def run_b200(args, world, rank, local_rank):
     cell_frac = cell_fp64_pipe_fraction(info.kernel_variant, info.pow_octaves, cells_evaluated, kernel_ms * 1e-3, peak_tf)
 
     # ---- phases and the pipelined variant ---------------------------------------------------------------
-    solver = ShardedSolver(plan, T_total, na, inp.T)
+    plan2 = VarPlan(inp, device=local_rank)        # two batches in flight need a plan (scratch) each
+    solver = ShardedSolver(plan, T_total, na, inp.T, second_plan=plan2)
     phases = solver.phase_us(d_day, alphas, ptf_mean=inp.ptf_mean, repeats=5)
     for _ in range(3):
         solver.step(d_day, alphas, ptf_mean=inp.ptf_mean)
@@ -450,8 +452,9 @@ def run_b200(args, world, rank, local_rank):
         },
         "phases_us": {k: round(v, 2) for k, v in phases.items()},
         "pipelined": {"value": pipelined_value, "unit": UNIT,
-                      "note": "ShardedSolver: all-gather + finalize of step i on a side stream under the solve of step i+1; "
-                              "whole K-step region between two events, no L2 flush between steps"},
+                      "note": "ShardedSolver, two batches in flight: consecutive steps alternate between two streams (a plan "
+                              "each), so a step's collective + finalize AND the partly idle end of its solve launch are covered "
+                              "by the next step's solve; whole K-step region between two events, no L2 flush between steps"},
         "iterations": iters_np,
         "plan": {"ctas_per_sm": info.ctas_per_sm, "threads_per_cta": info.threads_per_cta,
                  "smem_bytes_per_cta": info.smem_bytes_per_cta, "sm_count": info.sm_count,

@@ -75,21 +75,28 @@ def solve_sharded(plan, day_params_local: torch.Tensor, T_total: int, alphas, pt
 
 
 class ShardedSolver:
-    """Repeated sharded solves of batches of one shape, with the collective off the critical path.
+    """Repeated sharded solves of batches of one shape, two batches in flight.
 
-    A step's all-gather + finalize (latency-bound: ~20-30 us on 8 GPUs against a ~2 ms solve) runs on a side stream while
-    the NEXT step's solve kernel already runs on the caller's stream; two sets of buffers alternate.  Results of `step`
-    are valid on the side stream: call `synchronize()` (the caller's stream waits for it) before reading them.
-    `phase_us()` times the three phases of one step separately (CUDA events, no overlap) for the benchmark record.
+    Consecutive steps alternate between TWO streams, each with its own plan (a plan owns launch-order scratch and
+    iteration counters, so overlapping launches need one plan each) and its own buffers.  A step is solve kernel ->
+    all-gather -> finalize on its stream; while it drains, the next step's solve kernel is already running on the other
+    stream.  That hides the two things a lone batch pays for: the collective's latency (~20-30 us on 8 GPUs) and the
+    partly idle GPU at the end of every solve launch (a 1000-day launch is 3.4 waves of one-CTA days: SMs 93 % active).
+    Results of `step` are valid on the step's stream: call `synchronize()` (the caller's stream waits for both) before
+    reading them.  With a single plan the steps still alternate buffers but share one stream for the solves (only the
+    collective + finalize overlap).  `phase_us()` times the three phases of one step separately for the benchmark record.
     """
 
-    def __init__(self, plan, T_total: int, n_alpha: int, t_local: int, group=None):
+    def __init__(self, plan, T_total: int, n_alpha: int, t_local: int, group=None, second_plan=None):
+        self.plans = [plan, second_plan if second_plan is not None else plan]
         self.plan, self.T, self.na, self.group = plan, int(T_total), int(n_alpha), group
         self.sharded = dist.is_initialized() and dist.get_world_size(group) > 1
         self.world = dist.get_world_size(group) if self.sharded else 1
         self.per = -(-self.T // self.world)
         dev = torch.device("cuda", plan.device)
+        self.two_streams = second_plan is not None
         self.side = torch.cuda.Stream(device=dev)
+        self.streams = [torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)] if self.two_streams else None
         mk = lambda *shape, dtype: torch.empty(shape, dtype=dtype, device=dev)     # noqa: E731
         self.buffers = []
         for _ in range(2):
@@ -100,41 +107,55 @@ class ShardedSolver:
                 var=mk(self.na, self.T, dtype=torch.float64), case=mk(self.na, self.T, dtype=torch.int32),
                 iters=mk(self.na, dtype=torch.int32), free=None))
         self.t_local, self.flip = int(t_local), 0
-        plan.reserve(max(self.t_local, 1))
+        for pl in set(self.plans):
+            pl.reserve(max(self.t_local, 1))
 
-    def _solve(self, buf, day_local, alphas):
+    def _solve(self, plan, buf, day_local, alphas):
         # a ragged last block solves into a (n_alpha, t_local, 2) scratch and is copied into the padded block
         if buf["view"] is buf["local"]:
-            self.plan.solve_device(day_local, alphas, traj=buf["local"])
+            plan.solve_device(day_local, alphas, traj=buf["local"])
         else:
-            buf["local"][:, : self.t_local] = self.plan.solve_device(day_local, alphas)
+            buf["local"][:, : self.t_local] = plan.solve_device(day_local, alphas)
 
-    def _finish(self, buf, ptf_mean):
+    def _finish(self, plan, buf, ptf_mean):
         if self.sharded:
             dist.all_gather_into_tensor(buf["blocks"].view(-1), buf["local"].view(-1), group=self.group)
-            self.plan.finalize_device(buf["blocks"], ptf_mean=ptf_mean, var=buf["var"], case=buf["case"],
-                                      iterations=buf["iters"], T=self.T)
+            plan.finalize_device(buf["blocks"], ptf_mean=ptf_mean, var=buf["var"], case=buf["case"],
+                                 iterations=buf["iters"], T=self.T)
         else:
-            self.plan.finalize_device(buf["local"], ptf_mean=ptf_mean, var=buf["var"], case=buf["case"], iterations=buf["iters"])
+            plan.finalize_device(buf["local"], ptf_mean=ptf_mean, var=buf["var"], case=buf["case"], iterations=buf["iters"])
 
     def step(self, day_local: torch.Tensor, alphas, ptf_mean: float = 0.0):
-        buf = self.buffers[self.flip]
+        k = self.flip
+        buf, plan = self.buffers[k], self.plans[k]
         self.flip ^= 1
         main = torch.cuda.current_stream(self.side.device)
+        if self.two_streams:
+            ready = torch.cuda.Event()
+            ready.record(main)                    # the step's inputs are ready on the caller's stream
+            with torch.cuda.stream(self.streams[k]):
+                self.streams[k].wait_event(ready)
+                self._solve(plan, buf, day_local, alphas)      # stream order covers the reuse of this buffer set
+                self._finish(plan, buf, ptf_mean)
+            return buf["var"], buf["case"], buf["iters"]
         if buf["free"] is not None:
             main.wait_event(buf["free"])          # the side stream is done with this buffer set (two steps ago)
-        self._solve(buf, day_local, alphas)
+        self._solve(plan, buf, day_local, alphas)
         solved = torch.cuda.Event()
         solved.record(main)
         with torch.cuda.stream(self.side):
             self.side.wait_event(solved)
-            self._finish(buf, ptf_mean)
+            self._finish(plan, buf, ptf_mean)
             buf["free"] = torch.cuda.Event()
             buf["free"].record(self.side)
         return buf["var"], buf["case"], buf["iters"]
 
     def synchronize(self):
-        torch.cuda.current_stream(self.side.device).wait_stream(self.side)
+        main = torch.cuda.current_stream(self.side.device)
+        main.wait_stream(self.side)
+        if self.two_streams:
+            for st in self.streams:
+                main.wait_stream(st)
 
     def phase_us(self, day_local: torch.Tensor, alphas, ptf_mean: float = 0.0, repeats: int = 5) -> dict:
         """{'solve': us, 'gather': us, 'finalize': us}: one step's phases one after the other on the current stream."""
@@ -147,7 +168,7 @@ class ShardedSolver:
             if self.sharded:
                 dist.barrier(group=self.group)
             ev[0].record()
-            self._solve(buf, day_local, alphas)
+            self._solve(self.plan, buf, day_local, alphas)
             ev[1].record()
             if self.sharded:
                 dist.all_gather_into_tensor(buf["blocks"].view(-1), buf["local"].view(-1), group=self.group)
