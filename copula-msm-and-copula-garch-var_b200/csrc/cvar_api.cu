@@ -567,6 +567,9 @@ int cvar_plan_create(const cvar_desc_t* desc, const double* x, const double* dx,
     }
     double dx_min = INFINITY;
     for (int i = 1; i < n; ++i) dx_min = std::min(dx_min, x[i] - x[i - 1]);
+    // brackets whose image on the inner axis, (hi - lo) / w0, is shorter than the finest spacing hold at most one grid
+    // point per row (strip_pass_thin); 1 % margin for the rounding of the two bounds
+    kp.thin_width = (desc->w0 > 0.0 && std::getenv("CVAR_NO_THIN_PASS") == nullptr) ? 0.99 * dx_min * desc->w0 : 0.0;
     const double LOG2E = 1.4426950408889634;
     if (desc->copula == CVAR_COPULA_GAUSSIAN) {
         const double om = 1.0 - desc->rho * desc->rho;

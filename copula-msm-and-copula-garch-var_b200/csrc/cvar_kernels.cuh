@@ -97,6 +97,7 @@ struct KernelParams {
     const double* tq_table;      // student only
     const double* state_cdf;     // mixture: Phi(x_i / sigma_{a,s}), [2][q][n]
     const double* state_pdf;     // mixture: N(x_i; 0, sigma_{a,s}), [2][q][n]
+    double thin_width;           // a bisection bracket narrower than this (in q) holds at most one grid point per row
     unsigned long long* evaluated_cells;   // plan-wide counter of the cells the launches really evaluated (strips shared
                                            // between the alphas of a day are evaluated once): the roofline's numerator
 };
@@ -534,6 +535,7 @@ struct StripResult {
     double mass;
     unsigned cells;
     bool poisoned;
+    bool redo;   // strip_pass_thin met a row it cannot handle: the caller repeats the pass with strip_pass
 };
 
 struct Live {  // live window of rows / columns (cells outside have an infinite copula quantile)
@@ -545,7 +547,7 @@ struct Live {  // live window of rows / columns (cells outside have an infinite 
 // block-wide (cluster-wide when the day is split over a cluster) deterministic sum; every thread of every CTA
 // receives the same value
 __device__ __forceinline__ StripResult block_reduce(const Smem& S, const Part& pt, int& parity, double v, unsigned cells,
-                                                    bool poison) {
+                                                    bool poison, bool redo = false) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -554,7 +556,7 @@ __device__ __forceinline__ StripResult block_reduce(const Smem& S, const Part& p
         S.red[parity * MAX_CTA_WARPS + warp] = v;
         S.redc[parity * MAX_CTA_WARPS + warp] = cells;
     }
-    const int anyp = __syncthreads_or(poison ? 1 : 0);
+    const int anyp = __syncthreads_or((poison ? 1 : 0) | (redo ? 2 : 0));
     StripResult r;
     r.mass = 0.0;
     r.cells = 0;
@@ -563,7 +565,8 @@ __device__ __forceinline__ StripResult block_reduce(const Smem& S, const Part& p
         r.mass += S.red[parity * MAX_CTA_WARPS + w];
         r.cells += S.redc[parity * MAX_CTA_WARPS + w];
     }
-    r.poisoned = anyp != 0;
+    r.poisoned = (anyp & 1) != 0;
+    r.redo = (anyp & 2) != 0;
     if (pt.size > 1) {
         // publish this CTA's partial, then read every CTA's slot in rank order through distributed shared memory.
         // The slots are double-buffered by `parity`: a slot is rewritten two strips later, after the cluster barrier
@@ -704,7 +707,10 @@ __device__ __forceinline__ double sweep_rows(const KernelParams& P, const Smem& 
 // cnew[i] = count(q_new) for every owned row, searched inside [slo[i], shi[i]] (nullptr: open end), then the cells
 // [ca[i], cb[i]) of the row are summed; ca == nullptr is the constant lower end cmin, and ca / cb may alias cnew, slo or
 // shi -- the values then come from registers instead of a shared-memory round trip.
-template <int COPULA>
+// BISECT = true is the pass of a bisection step with positive w0: both bracket ends exist, the boundary sought lies between
+// them (midpoint search) and the strip is the lower (ca == slo) or the upper half of the bracket -- known at compile time,
+// which spares every row the pointer comparisons and selects of the general form.
+template <int COPULA, bool BISECT = false>
 __device__ StripResult strip_pass(const KernelParams& P, const Smem& S, const Part& pt, const Live& L, int& parity,
                                   double q_new, u16* cnew, const u16* slo, const u16* shi, const u16* ca,
                                   const u16* cb, bool poison_mode) {
@@ -712,15 +718,22 @@ __device__ StripResult strip_pass(const KernelParams& P, const Smem& S, const Pa
     double total = 0.0;
     unsigned cells = 0;
     bool poison = false;
-    const bool between = slo && shi && P.w0 > 0.0;   // both bracket ends known and ordered: midpoint search
+    const bool between = BISECT || (slo && shi && P.w0 > 0.0);   // both bracket ends known and ordered: midpoint search
+    const bool lower = ca == slo;
     for (int m = 0; m < owned_rounds(pt, n); ++m) {
         const int i = owned_row(pt, m);
         int s = 0, e = 0;
         if (i < n) {
             const double xi = S.xs[i];
-            const int lo = slo ? (int)slo[i] : 0, hi = shi ? (int)shi[i] : n;
+            const int lo = (BISECT || slo) ? (int)slo[i] : 0, hi = (BISECT || shi) ? (int)shi[i] : n;
             int k = lo;
-            if (!(slo && shi && lo == hi)) {   // else: no grid point of this row between the bracket ends, nothing can move
+            if (BISECT) {
+                if (lo != hi) {   // else: no grid point of this row between the bracket ends, nothing can move
+                    k = max(count_between(S.xs, inner_bound(q_new, xi, P.w0, P.w1, P.rw0_exact), lo, hi), P.cmin);
+                    s = lower ? lo : k;
+                    e = lower ? k : hi;
+                }
+            } else if (!(slo && shi && lo == hi)) {
                 if (between)
                     k = max(count_between(S.xs, inner_bound(q_new, xi, P.w0, P.w1, P.rw0_exact), lo, hi), P.cmin);
                 else
@@ -784,6 +797,56 @@ __device__ StripResult strip_pass(const KernelParams& P, const Smem& S, const Pa
     return r;
 }
 
+// A pass of the late bisection steps, where the bracket is narrower than the finest axis spacing: every row's bracket
+// [lo, hi] holds at most ONE grid point (hi <= lo + 1), so the new boundary is one comparison and the strip holds one
+// cell of the row or none.  Straight-line code, a third of the instructions of the general pass for such rows (the
+// bookkeeping of a pass is bound by instruction issue).  `lower`: the strip is the lower half
+// [lo, mid) of the bracket, else the upper half [mid, hi).  A row with hi > lo + 1 (cannot happen for a bracket below
+// thin_width; checked all the same) makes the whole CTA repeat the pass with strip_pass.
+template <int COPULA>
+__device__ StripResult strip_pass_thin(const KernelParams& P, const Smem& S, const Part& pt, const Live& L, int& parity,
+                                       double q_new, u16* cnew, const u16* slo, const u16* shi, bool lower, bool poison_mode) {
+    const int n = P.n;
+    double total = 0.0;
+    unsigned cells = 0;
+    bool poison = false, redo = false;
+    for (int m = 0; m < owned_rounds(pt, n); ++m) {
+        const int i = owned_row(pt, m);
+        if (i >= n) continue;
+        const int lo = (int)slo[i], hi = (int)shi[i];
+        int k = lo;
+        if (lo != hi) {
+            if (hi - lo > 1) redo = true;
+            const double g = inner_bound(q_new, S.xs[i], P.w0, P.w1, P.rw0_exact);
+            k = (S.xs[lo] <= g) ? hi : lo;   // counts are clipped at cmin already: lo >= cmin
+            if (lower ? (k == hi) : (k == lo)) {   // the strip holds the cell (i, lo)
+                cells += 1u;
+                bool live = true;
+                if (!L.full) {
+                    live = i >= L.i_lo && i < L.i_hi && lo >= L.j_lo && lo < L.j_hi;
+                    poison = poison || !live;
+                }
+                if (live) {
+                    Row<COPULA> row;
+                    row.load(P, S, i);
+                    const double2 v = S.in[lo];
+                    bool fast = false;
+                    if (kv_pow_degree(COPULA) > 0 && POW_FAST_MODE > 0 && P.pow_octaves > 0)
+                        fast = L.day_fast || row.quad_form(v.x) < P.pow_fast_limit;
+                    const double w = (kv_pow_degree(COPULA) > 0 && POW_FAST_MODE > 0 && fast)
+                                         ? row.template add_cell<true>(P, S, v.x, v.y, 0.0)
+                                         : row.template add_cell<false>(P, S, v.x, v.y, 0.0);
+                    total = fma(row.fac, w, total);
+                }
+            }
+        }
+        cnew[i] = (u16)k;
+    }
+    StripResult r = block_reduce(S, pt, parity, total, cells, poison && poison_mode, redo);
+    if (r.poisoned) r.mass = NAN;
+    return r;
+}
+
 // strip_pass with reuse across the alphas of a day.  `memo_n` (uniform across the CTA) counts the entries written
 // so far (by thread 0, right after a strip's reduction); only the first `memo_visible` of them -- those of
 // earlier alphas, published by the barrier at the top of the alpha loop -- are searched.
@@ -793,7 +856,7 @@ __device__ __forceinline__ StripResult strip_memo(const KernelParams& P, const S
                                                   double a, double b,
                                                   double q_new, u16* cnew, const u16* slo, const u16* shi,
                                                   const u16* ca, const u16* cb, bool poison_mode,
-                                                  unsigned long long& evaluated) {
+                                                  unsigned long long& evaluated, bool thin = false, bool bisect = false) {
     if (use_memo) {
         for (int k = 0; k < memo_visible; ++k) {
             const double* e = S.memo + 4 * k;
@@ -807,7 +870,15 @@ __device__ __forceinline__ StripResult strip_memo(const KernelParams& P, const S
             }
         }
     }
-    const StripResult r = strip_pass<COPULA>(P, S, pt, L, parity, q_new, cnew, slo, shi, ca, cb, poison_mode);
+    StripResult r;
+    r.redo = true;
+    if (thin) r = strip_pass_thin<COPULA>(P, S, pt, L, parity, q_new, cnew, slo, shi, ca == slo, poison_mode);
+    if (r.redo) {
+        if (bisect)
+            r = strip_pass<COPULA, true>(P, S, pt, L, parity, q_new, cnew, slo, shi, ca, cb, poison_mode);
+        else
+            r = strip_pass<COPULA, false>(P, S, pt, L, parity, q_new, cnew, slo, shi, ca, cb, poison_mode);
+    }
     evaluated += r.cells;
     if (use_memo && remember && memo_n < MEMO_SIZE) {
         if (threadIdx.x == 0) {
@@ -936,8 +1007,11 @@ solve_kernel(KernelParams P, const double* __restrict__ day_params, long long da
 #endif
                 const double mid = (lo + hi) / 2;
                 const double a = stack ? lo : mid, b = stack ? mid : hi;
+                // bracket narrower than the finest axis spacing: at most one grid point per row between its ends
+                const bool thin = !CLUSTER && P.thin_width > 0.0 && (hi - lo) < P.thin_width;
                 const StripResult s = strip_memo<COPULA>(P, S, pt, L, parity, use_memo, k < MEMO_PER_ALPHA - 1, memo_visible, memo_n, a, b,
-                                                         mid, cm, cl, ch, stack ? cl : cm, stack ? cm : ch, poison_mode, evaluated);
+                                                         mid, cm, cl, ch, stack ? cl : cm, stack ? cm : ch, poison_mode, evaluated, thin,
+                                                         P.w0 > 0.0);
                 ncell += s.cells;
                 const double r_prev = R;
                 R = (a == prev_upper) ? R + s.mass : R - s.mass;  // adjust_integral (:241-246)
