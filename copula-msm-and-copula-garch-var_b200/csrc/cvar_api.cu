@@ -62,7 +62,6 @@ struct cvar_plan {
     size_t sort_tmp_bytes;
     double rho_eff;
     int order_min_waves;   // a chunk is ordered when it has more days than this many waves of resident CTAs
-    bool order_arranged;   // arranged_source() on top of the most-expensive-first order
 };
 
 #define CU_TRY(expr)                          \
@@ -245,12 +244,8 @@ int reserve_chunk(cvar_plan* p, int64_t days) {
     return 0;
 }
 
-// Chunks longer than this many waves are simply started most-expensive-first: their tail is a small share of the launch.
-constexpr int ORDER_ARRANGED_MAX_WAVES = 16;
-
-// Launch order of a chunk: ascending portfolio-variance proxy (most expensive solves first), then arranged so that the
-// slots which run one day more than the others run cheap days (arranged_source, cvar_kernels.cuh); nullptr when the
-// chunk (nearly) fits the resident CTA slots anyway.  Works in the scratch reserved for chunk_days days.
+// Launch order of a chunk: ascending portfolio-variance proxy (most expensive solves first); nullptr when the chunk
+// (nearly) fits the resident CTA slots anyway.  Works in the scratch reserved for chunk_days days.
 int make_order(cvar_plan* p, const double* d_day, int64_t T, cudaStream_t st, const int** order_out) {
     *order_out = nullptr;
     const int64_t slots = (int64_t)p->sm_count * std::max(p->ctas_per_sm, 1);
@@ -268,11 +263,6 @@ int make_order(cvar_plan* p, const double* d_day, int64_t T, cudaStream_t st, co
     CU_TRY(cudaGetLastError());
     CU_TRY(cub::DeviceRadixSort::SortPairs(tmp, b_tmp, key_in, key_out, idx_in, idx_out, (int)T, 0, 32, st));
     *order_out = idx_out;
-    if (p->order_arranged && T % slots != 0 && T / slots <= ORDER_ARRANGED_MAX_WAVES) {
-        arrange_order_kernel<<<(unsigned)((T + 255) / 256), 256, 0, st>>>(idx_out, idx_in, (int)T, (int)slots);
-        CU_TRY(cudaGetLastError());
-        *order_out = idx_in;   // the unsorted indices are no longer needed
-    }
     return 0;
 }
 
@@ -342,10 +332,15 @@ int launch_solve_kernel(cvar_plan* p, int cluster, int threads, int64_t units, c
 // second kernel on another stream, so that the tail of the launch is made of shorter units.  c3: 1.78 -> 1.82-1.91 ms for
 // 100-400 tail days; the cluster barrier per strip and the second axis stage cost more than the idle SMs of the tail.
 // Also tried: the remainder of the chunk modulo the resident CTA slots (112 of 1000 days) as CTAs of twice the threads, one
-// per SM: 1.776 -> 1.804 ms -- a wide CTA only starts on an SM once BOTH of its slots have drained.  A simulation of the
-// launch with the measured per-day costs gives 1.16 x the time per day of a long batch for 1000 days on 296 slots when
-// the days are started most-expensive-first (1.07 for 2000 days, 1.02 for 8000): the quantisation of 3.4 waves.  What does
-// help is WHICH slots run the fourth day: arranged_source, cvar_kernels.cuh.)
+// per SM: 1.776 -> 1.804 ms -- a wide CTA only starts on an SM once BOTH of its slots have drained.
+// The CTA timeline of c3 (tools/timeline_profile.py, profiles/r2_c3_timeline.txt): 1000 days on 296 slots, CTA durations
+// 184 .. 710 us (mean 433) inside a 1647 us launch, 263 of 296 slots busy on average; all slots are busy until 85 % of the
+// launch, the rest is the last day of each slot running out.  Replaying the launch with the measured durations gives
+// 1644 us for this order and 1640 us for most-expensive-first on the TRUE durations: with 3.4 days per slot and a 4 x
+// spread of durations the loss is the packing, not the proxy.  Tried on top: an arranged order that feeds the 112 slots
+// which run a fourth day with cheap days only (1.686 -> 1.741 ms at 1000 days, 1.223 -> 1.266 at 700, 2.451 -> 2.393 at
+// 1500; c4 unchanged) and ordering c2's 1.7 waves (1.225 -> 1.228 ms): neither kept.  Two batches in flight
+// (ShardedSolver) are what fills the tail: DESIGN.md section 8.)
 int launch_solve(cvar_plan* p, const double* d_day, int64_t T, const AlphaSet& A, uint32_t* d_traj, double* d_mass,
                  unsigned long long* d_cells, cudaStream_t st) {
     for (int64_t c0 = 0; c0 < T; c0 += p->chunk_days) {
@@ -405,14 +400,6 @@ extern "C" {
 int cvar_abi_version(void) { return CVAR_ABI_VERSION; }
 
 int cvar_check_dim(int32_t dim) { return dim == 2 ? CVAR_OK : CVAR_ERR_DIM; }
-
-int cvar_launch_order(int64_t days, int32_t slots, int32_t* rank_out) {
-    if (days > 0 && !rank_out) return CVAR_ERR_NULL;
-    if (days < 0 || days > 0x7fffffffLL || slots <= 0) return CVAR_ERR_SIZE;
-    const bool arranged = days % slots != 0 && days / slots <= ORDER_ARRANGED_MAX_WAVES;
-    for (int64_t p = 0; p < days; ++p) rank_out[p] = arranged ? arranged_source((int)p, (int)days, slots) : (int32_t)p;
-    return CVAR_OK;
-}
 
 void cvar_desc_default(cvar_desc_t* d) {
     if (!d) return;
@@ -779,9 +766,7 @@ int cvar_plan_create(const cvar_desc_t* desc, const double* x, const double* dx,
     }
 #undef CVAR_CLUSTER_OCC
     p->order_min_waves = 2;
-    p->order_arranged = true;
     if (const char* env = std::getenv("CVAR_ORDER_MIN_WAVES")) p->order_min_waves = std::max(1, std::atoi(env));   // tuning knobs
-    if (const char* env = std::getenv("CVAR_LAUNCH_ORDER")) p->order_arranged = std::strcmp(env, "sorted") != 0;
     {   // launch-order scratch for the default chunk; cvar_plan_reserve (or a *_host call) sizes it for larger batches
         int64_t days = 65536;
         if (const char* env = std::getenv("CVAR_CHUNK_DAYS")) days = std::max(1LL, std::atoll(env));

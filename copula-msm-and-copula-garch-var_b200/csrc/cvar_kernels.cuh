@@ -925,6 +925,10 @@ solve_kernel(KernelParams P, const double* __restrict__ day_params, long long da
     const long long prof_t0 = clock64();
     long long prof_thin = 0, prof_probe = 0;
 #endif
+#ifdef CVAR_PROFILE_TIMELINE   // experiment: where and when each CTA ran (results are overwritten): tools/timeline_profile.py
+    unsigned long long tl_start;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tl_start));
+#endif
     const bool day_fast = stage0<COPULA>(P, day_params + day * stride, S);
 #ifdef CVAR_PROFILE_PHASES
     const long long prof_t1 = clock64();
@@ -1038,6 +1042,16 @@ solve_kernel(KernelParams P, const double* __restrict__ day_params, long long da
             if (mass_out) mass_out[o] = (double)prof_probe;       // probes + bracket set-up
             if (cells_out) cells_out[o] = (unsigned long long)(clock64() - prof_t0);
 #endif
+#ifdef CVAR_PROFILE_TIMELINE
+            unsigned smid;
+            unsigned long long tl_end;
+            asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
+            asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tl_end));
+            traj[2 * o] = smid;
+            traj[2 * o + 1] = blockIdx.x;
+            if (mass_out) mass_out[o] = (double)tl_start;          // ns; exact below 2^53
+            if (cells_out) cells_out[o] = tl_end;
+#endif
         }
     }
     if (P.evaluated_cells && threadIdx.x == 0 && pt.rank == 0) atomicAdd(P.evaluated_cells, evaluated);
@@ -1104,34 +1118,6 @@ __global__ void order_key_kernel(KernelParams P, const double* __restrict__ day_
     const double var_p = P.w0 * P.w0 * v[0] + P.w1 * P.w1 * v[1] + 2.0 * rho_eff * P.w0 * P.w1 * sqrt(v[0] * v[1]);
     key[d] = (float)fmax(var_p, 0.0);
     idx[d] = (int)d;
-}
-
-// A chunk of T days on `slots` resident CTA slots runs q = T / slots full waves and a remainder of r days.  Started
-// most-expensive-first, the r cheapest days all start last, on slots that have already run q days: the launch ends
-// with r busy slots and slots - r idle ones (c3, 1000 days on 296 slots: 1.16 x the time per day of a long batch).
-// Arranged order: the r slots that will run q + 1 days should run CHEAP days only, the others q expensive days each.
-// CTAs go to whichever slot frees first, so the list is written in the order those slots free up:
-//     [ round 0 of the expensive class | round 0 of the cheap class | cheap 1 | expensive 1 | cheap 2 | ... | cheap q ]
-// (expensive rounds have slots - r days, cheap rounds r days; odd rounds are reversed so that a slot that drew the
-// largest day of one round draws the smallest of the next).  arranged_source(p) is the rank, in the
-// most-expensive-first order, of the day started p-th.  Simulated with the per-day costs of c3 (tools/launch_order_sim.py):
-// 1.16 -> 1.05 x; measured: DESIGN.md section 8.
-__host__ __device__ inline int arranged_source(int p, int T, int slots) {
-    const int q = T / slots, r = T % slots;
-    if (q == 0 || r == 0) return p;
-    const int big = slots - r;      // slots that run q days
-    const int n_big = big * q;      // days of the expensive class
-    if (p < big) return p;
-    if (p < slots) return n_big + (p - big);
-    const int pp = p - slots, j = 1 + pp / slots, o = pp % slots;
-    if (o < r) return n_big + j * r + ((j & 1) ? r - 1 - o : o);
-    const int e = o - r;
-    return j * big + ((j & 1) ? big - 1 - e : e);
-}
-
-__global__ void arrange_order_kernel(const int* __restrict__ sorted, int* __restrict__ out, int T, int slots) {
-    const int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p < T) out[p] = sorted[arranged_source(p, T, slots)];
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -50,7 +50,6 @@ _PROTOTYPES = {
     "cvar_abi_version": (C.c_int, []),
     "cvar_desc_default": (None, [C.POINTER(CvarDesc)]),
     "cvar_check_dim": (C.c_int, [C.c_int32]),
-    "cvar_launch_order": (C.c_int, [C.c_int64, C.c_int32, C.POINTER(C.c_int32)]),
     "cvar_strerror": (C.c_char_p, [C.c_int]),
     "cvar_plan_create": (C.c_int, [C.POINTER(CvarDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]),
     "cvar_plan_destroy": (C.c_int, [C.c_void_p]),

@@ -148,7 +148,6 @@ typedef struct cvar_plan_info {
  *                              costing the SM a resident warp, none below four)
  *   CVAR_CHUNK_DAYS=N          days per launch of the solve kernel a new plan reserves scratch for (cvar_plan_reserve)
  *   CVAR_TQ_BUDGET=x           accuracy budget of the Student-t quantile table (default 1e-11; tests force a refusal)
- *   CVAR_LAUNCH_ORDER=sorted   start the days of a chunk most-expensive-first only (default "arranged": see cvar_launch_order)
  *   CVAR_ORDER_MIN_WAVES=k     chunks of at most k waves of resident CTAs are started in their natural order (default 2)
  * Read by the Python layers: CVAR_BACKEND=b200|reference (factory default).
  * The Python loader additionally honours CVAR_B200_LIB=<path to an alternative libcvar_b200.so>.
@@ -191,14 +190,6 @@ int cvar_plan_get_info(const cvar_plan_t* plan, cvar_plan_info_t* info_out);
  * synchronises the plan's stream when it reallocates.  (No counterpart in the reference.)
  */
 int cvar_plan_reserve(cvar_plan_t* plan, int64_t days);
-/*
- * The launch order of a chunk of `days` days on `slots` resident CTA slots (SMs x CTAs per SM of the plan), as ranks:
- * rank_out[p] is the position, in the most-expensive-first order of the chunk, of the day whose CTA is started p-th.
- * Slots that will run one day more than the others are fed the cheap days (cvar_kernels.cuh, arranged_source).  The order
- * never changes a result; this host-side copy of the device routine exists so that it can be tested without a GPU (it must
- * be a permutation for every days / slots).  (No counterpart in the reference, whose days run one after the other.)
- */
-int cvar_launch_order(int64_t days, int32_t slots, int32_t* rank_out);
 
 /*
  * Strip masses: out[t] = S(bounds[t][0], bounds[t][1]) for day t.

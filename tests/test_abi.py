@@ -131,55 +131,3 @@ def test_dimension_decision_is_a_status_code(lib):
     assert b"two-asset" in lib.cvar_strerror(-10)
     with pytest.raises(NotImplementedError, match="two-asset"):
         _lib.check_dim(3)
-
-
-def _launch_ranks(lib, days, slots):
-    out = np.empty(days, dtype=np.int32)
-    assert lib.cvar_launch_order(days, slots, out.ctypes.data_as(C.POINTER(C.c_int32))) == 0
-    return out
-
-
-def test_launch_order_is_a_permutation_for_every_batch_size(lib):
-    """The arranged launch order (cvar_kernels.cuh, arranged_source) starts every day of a chunk exactly once."""
-    rng = np.random.default_rng(5)
-    cases = [(d, s) for s in (1, 2, 7, 148, 296, 592) for d in (0, 1, s - 1, s, s + 1, 2 * s - 1, 2 * s + 1, 3 * s + s // 2, 17 * s + 3)]
-    cases += [(int(rng.integers(1, 20000)), int(rng.integers(1, 1200))) for _ in range(200)]
-    for days, slots in cases:
-        if days < 0:
-            continue
-        ranks = _launch_ranks(lib, days, slots)
-        assert np.array_equal(np.sort(ranks), np.arange(days)), (days, slots)
-    assert lib.cvar_launch_order(-1, 8, None) == -5 and lib.cvar_launch_order(8, 0, None) == -1
-
-
-def test_launch_order_feeds_the_extra_wave_with_cheap_days(lib):
-    """c3's shape: 1000 days on 296 slots = 3 waves + 112.  The 112 slots that run a fourth day must see only days of the
-    cheap class (the 448 highest ranks), the other 184 only expensive ones; whole waves and long chunks stay sorted."""
-    days, slots = 1000, 296
-    ranks = _launch_ranks(lib, days, slots)
-    q, r = divmod(days, slots)
-    n_expensive = (slots - r) * q
-    cheap = ranks >= n_expensive
-    assert cheap.sum() == r * (q + 1)
-    # list scheduling with any cost that falls with the rank: replay the launch on `slots` slots and record who ran what
-    import heapq
-    cost = 1.3 - 0.5 * np.arange(days) / days
-    heap = [(0.0, s) for s in range(slots)]
-    ran = [[] for _ in range(slots)]
-    for p in range(days):
-        t, s = heapq.heappop(heap)
-        ran[s].append(int(ranks[p]))
-        heapq.heappush(heap, (t + cost[ranks[p]], s))
-    four = [days_ for days_ in ran if len(days_) == q + 1]
-    three = [days_ for days_ in ran if len(days_) == q]
-    assert len(four) == r and len(three) == slots - r
-    assert all(rank >= n_expensive for days_ in four for rank in days_)
-    assert all(rank < n_expensive for days_ in three for rank in days_)
-    finish = max(t for t, _ in heap)
-    sorted_heap = [0.0] * slots
-    heapq.heapify(sorted_heap)
-    for p in range(days):
-        heapq.heappush(sorted_heap, heapq.heappop(sorted_heap) + cost[p])
-    assert finish < 0.95 * max(sorted_heap)      # the point of the arrangement
-    for d, s in ((592, 296), (20 * 296 + 5, 296), (100, 296)):
-        assert np.array_equal(_launch_ranks(lib, d, s), np.arange(d))

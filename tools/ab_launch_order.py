@@ -23,10 +23,8 @@ from cvar_b200.backend import VarPlan           # noqa: E402
 
 SETTINGS = {
     "natural": {"CVAR_ORDER_MIN_WAVES": "1000000"},
-    "sorted": {"CVAR_LAUNCH_ORDER": "sorted"},
-    "arranged": {},
-    "sorted_from_1_wave": {"CVAR_LAUNCH_ORDER": "sorted", "CVAR_ORDER_MIN_WAVES": "1"},
-    "arranged_from_1_wave": {"CVAR_ORDER_MIN_WAVES": "1"},
+    "sorted": {},
+    "sorted_from_1_wave": {"CVAR_ORDER_MIN_WAVES": "1"},
 }
 
 
