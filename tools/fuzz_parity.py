@@ -1,6 +1,6 @@
 """One-off wide parity fuzz on a GPU box: random small configurations, CUDA solve vs the CPU oracle.
 
-    python tools/fuzz_parity.py [first_seed] [count]
+    python tools/fuzz_parity.py [first_seed] [count] [max_seconds]
 
 Prints one JSON line: solves checked, bit-identical solves, max |dVaR|, per-family mismatch list.
 """
@@ -19,10 +19,17 @@ from oracle import var_oracle as vo                # noqa: E402
 
 first = int(sys.argv[1]) if len(sys.argv) > 1 else 100
 count = int(sys.argv[2]) if len(sys.argv) > 2 else 300
+max_seconds = float(sys.argv[3]) if len(sys.argv) > 3 else float("inf")   # stop early (and still report) after this long
+import time                                        # noqa: E402
+t_start = time.perf_counter()
+seeds_done = 0
 solves = exact = 0
 worst = 0.0
 bad = []
 for seed in range(first, first + count):
+    if time.perf_counter() - t_start > max_seconds:
+        break
+    seeds_done += 1
     inp, alphas = _random_case(seed)
     with VarPlan(inp) as plan:
         res = plan.solve(inp.day_params(), alphas, ptf_mean=inp.ptf_mean)
@@ -38,4 +45,4 @@ for seed in range(first, first + count):
         worst = max(worst, float(d.max()))
         if d.max() > 0:
             bad.append({"seed": seed, "alpha": a, "copula": inp.copula, "marginal": inp.marginal, "n": inp.n, "max_abs": float(d.max())})
-print(json.dumps({"cases": count, "solves": solves, "bit_identical": exact, "max_abs_dvar": worst, "not_identical": bad}))
+print(json.dumps({"first_seed": first, "cases": seeds_done, "solves": solves, "bit_identical": exact, "max_abs_dvar": worst, "not_identical": bad}))
